@@ -1,0 +1,147 @@
+/*
+ * snappier_b200.h -- C ABI of the B200-native Snappy block engine.
+ *
+ * This is the drop-in boundary for Snappier's block path.  Snappier itself has
+ * no FFI seam (it is 100 % managed C#); the seam is the pair of internal calls
+ * that `Snappy.cs` makes into `SnappyCompressor` / `SnappyDecompressor`.  Each
+ * entry point below names the reference interface it replaces (paths relative
+ * to /root/reference/Snappier/).  INTEGRATION.md shows the P/Invoke stub.
+ *
+ * Plain C: pointers, sizes, fixed-width integers.  No torch / C++ types.
+ * All functions are thread-safe; per-thread CUDA resources are created lazily.
+ * There is NO CPU fallback: without a usable CUDA device every compute entry
+ * point returns SNP_E_NO_DEVICE.
+ */
+#ifndef SNAPPIER_B200_H
+#define SNAPPIER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNP_ABI_VERSION 1
+
+/* ---- per-block status (>= 0).  The C# shim maps them to the reference's
+ *      exceptions exactly as listed. ------------------------------------- */
+enum snp_status {
+    SNP_OK = 0,
+    /* Try* return false; Compress/Decompress throw
+     * ArgumentException("Output buffer is too small.") -- ThrowHelper.cs:18-19 */
+    SNP_OUTPUT_TOO_SMALL = 1,
+    /* "Invalid stream length": InvalidDataException from GetUncompressedLength
+     * (VarIntEncoding.Read.cs:20), InvalidOperationException from Decompress
+     * (SnappyDecompressor.cs:53-56) */
+    SNP_INVALID_LENGTH = 2,
+    /* InvalidDataException("Incomplete Snappy block.") -- ThrowHelper.cs:27-28 */
+    SNP_INCOMPLETE = 3,
+    /* InvalidDataException("Invalid copy offset") -- SnappyDecompressor.cs:600 */
+    SNP_INVALID_COPY_OFFSET = 4,
+    /* InvalidDataException("Data too long") -- SnappyDecompressor.cs:572,605 */
+    SNP_DATA_TOO_LONG = 5
+};
+
+/* ---- call-level errors (< 0) ------------------------------------------ */
+enum snp_error {
+    SNP_E_CUDA = -1,        /* a CUDA call failed; see snp_last_error() */
+    SNP_E_INVALID_ARG = -2, /* null pointer / bad enum / overlap */
+    SNP_E_NO_DEVICE = -3,   /* no CUDA device or kernel image not loadable */
+    SNP_E_OVERLAP = -4      /* input and output overlap -> InvalidOperationException
+                               ("Input and output spans must not overlap.",
+                               SnappyCompressor.cs:27-30) */
+};
+
+/* Hash used by the compressor's match finder (HashTable.cs:91-126).  Snappier
+ * picks it per platform, so the compressed BYTES differ per platform:
+ *   CRC32C : x64 with SSE4.2 / ARM64 with CRC, .NET 8+       (HashTable.cs:109-117)
+ *   MUL    : netstandard2.0 / net472 / intrinsics disabled   (HashTable.cs:120-123) */
+enum snp_hash_mode { SNP_HASH_CRC32C = 0, SNP_HASH_MUL = 1 };
+
+/* Where the buffers of a batched call live. */
+enum snp_mem_kind {
+    SNP_MEM_HOST = 0,   /* every pointer is host memory; call is synchronous   */
+    SNP_MEM_DEVICE = 1  /* every pointer is device memory of the context's GPU;
+                           work is enqueued on `stream` and the call returns    */
+};
+
+#define SNP_BLOCK_SIZE 65536u /* Constants.cs:25-26 */
+
+int snp_abi_version(void);
+const char *snp_status_string(int status);
+/* Thread-local text of the last SNP_E_CUDA on this thread ("" if none). */
+const char *snp_last_error(void);
+
+/* ---- sizing ------------------------------------------------------------ */
+/* Helpers.MaxCompressedLength (Helpers.cs:17-46): 32 + n + n/6 + 1. */
+int32_t snp_max_compressed_length(int32_t n);
+/* Snappy.GetMaxCompressedLength (Snappy.cs:20-24): the above + 5. */
+int32_t snp_get_max_compressed_length(int32_t n);
+/* Snappy.GetUncompressedLength (Snappy.cs:142-143).  Pure host varint read. */
+int snp_uncompressed_length(const uint8_t *in, size_t n, uint32_t *len);
+
+/* ---- contexts ---------------------------------------------------------- */
+/* One context = one GPU + one private stream + reusable staging buffers.  A
+ * context may be used by one thread at a time (calls on it are serialised by
+ * an internal mutex).  The single-call API below uses a lazily created
+ * thread-local context on the current device. */
+typedef struct snp_ctx snp_ctx;
+int snp_create(int device, snp_ctx **ctx);
+void snp_destroy(snp_ctx *ctx);
+int snp_ctx_device(const snp_ctx *ctx);
+/* Number of kernel launches this context has issued (bench: gpu_launches). */
+uint64_t snp_ctx_launch_count(const snp_ctx *ctx);
+
+/* ---- single-call API: host buffers, synchronous ------------------------ */
+/* Replaces SnappyCompressor.TryCompress(ReadOnlySpan<byte>, Span<byte>, out int)
+ * (SnappyCompressor.cs:24-83) as called by Snappy.TryCompress (Snappy.cs:55-67).
+ * Any input length < 2^32; inputs above 64 KiB are split into independent
+ * 64 KiB fragments exactly like the reference (SnappyCompressor.cs:40-80).
+ * SNP_OUTPUT_TOO_SMALL -> *written = 0 (SnappyCompressor.cs:63-68). */
+int snp_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written,
+                 uint32_t hash_mode);
+
+/* Replaces the one-shot use of SnappyDecompressor in Snappy.TryDecompress
+ * (Snappy.cs:172-186): Decompress -> AllDataDecompressed -> Read -> EndOfFile.
+ * Data errors take precedence over SNP_OUTPUT_TOO_SMALL, and on TOO_SMALL the
+ * first `cap` bytes are still written (SnappyDecompressor.Read, :613-629). */
+int snp_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written);
+
+/* ---- batched API: the throughput path (an extension; the reference has no
+ *      batch call -- each item is one independent Snappy.Compress/Decompress) --
+ *
+ * Item i reads  in_base  + in_off[i]  .. + in_len[i]
+ *        writes out_base + out_off[i] .. + out_cap[i]   (capacity)
+ * and reports out_len[i] (bytes produced; 0 unless status[i] == SNP_OK) and
+ * status[i] (enum snp_status).  A bad item never affects its neighbours.
+ * Item regions must not overlap each other or the input.
+ *
+ * compress: in_len[i] <= SNP_BLOCK_SIZE (one fragment per item, one warp per
+ *   item); give each item snp_get_max_compressed_length(in_len[i]) of capacity
+ *   to make SNP_OUTPUT_TOO_SMALL impossible.  Larger inputs: snp_compress().
+ * decompress: each item is a complete block with its own varint header.
+ *
+ * ctx == NULL uses the calling thread's default context.  `stream` is a
+ * cudaStream_t (NULL = the context's own stream); used for SNP_MEM_DEVICE
+ * only.  Return: SNP_OK once the work is done (HOST) / enqueued (DEVICE),
+ * or a negative snp_error.  Per-item failures are NOT a call failure. */
+int snp_compress_batch(snp_ctx *ctx, const uint8_t *in_base, const uint64_t *in_off,
+                       const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off,
+                       const uint32_t *out_cap, uint32_t *out_len, int32_t *status, size_t n_items,
+                       uint32_t hash_mode, int mem_kind, void *stream);
+
+int snp_decompress_batch(snp_ctx *ctx, const uint8_t *in_base, const uint64_t *in_off,
+                         const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off,
+                         const uint32_t *out_cap, uint32_t *out_len, int32_t *status,
+                         size_t n_items, int mem_kind, void *stream);
+
+/* Batched Snappy.GetUncompressedLength: ulen[i] / status[i] per item. */
+int snp_uncompressed_length_batch(snp_ctx *ctx, const uint8_t *in_base, const uint64_t *in_off,
+                                  const uint32_t *in_len, uint32_t *ulen, int32_t *status,
+                                  size_t n_items, int mem_kind, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAPPIER_B200_H */

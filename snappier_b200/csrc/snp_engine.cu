@@ -1,0 +1,593 @@
+// snp_engine.cu -- host side of the C ABI in include/snappier_b200.h.
+//
+// Contexts, staging, launches.  All arithmetic of the Snappy block path runs in
+// the CUDA kernels included below; there is no CPU implementation here (the
+// only host-side arithmetic is the 1..5-byte varint length prefix, which the
+// reference also reads before it decides how much memory to rent,
+// SnappyDecompressor.cs:110-173).
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "snp_common.cuh"
+#include "snp_compress_v1.cuh"
+#include "snp_decompress_v1.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int cuda_fail(cudaError_t e, const char *what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed at snp_engine.cu:%d: %s (%s)", what, line, cudaGetErrorName(e),
+             cudaGetErrorString(e));
+    g_last_error = buf;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNoKernelImageForDevice ||
+        e == cudaErrorInvalidDevice)
+        return SNP_E_NO_DEVICE;
+    return SNP_E_CUDA;
+}
+
+#define CU(call)                                               \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call, __LINE__); \
+    } while (0)
+
+struct DevBuf {  // grow-only device scratch
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return SNP_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            want = n;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)", __LINE__);
+        cap = want;
+        return SNP_OK;
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+}  // namespace
+
+struct snp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::atomic<uint64_t> launches{0};
+    int sm_count = 148;
+    int decomp_kernel = 1;  // SNP_DECOMP_KERNEL
+    int comp_kernel = 1;    // SNP_COMP_KERNEL
+    DevBuf d_in, d_out, d_meta, d_tmp;
+    bool attrs_set = false;
+};
+
+namespace {
+
+constexpr int kCompWarps = 7;  // 7 x 32 KiB tables + 2 KiB LUT = 226 KiB <= 227 KiB
+constexpr size_t kCompSmem = (size_t)kCompWarps * 32768 + 2048;
+
+int ctx_set_attrs(snp_ctx *c) {
+    if (c->attrs_set) return SNP_OK;
+    CU(cudaFuncSetAttribute(snp::k_compress_v1<SNP_HASH_CRC32C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kCompSmem));
+    CU(cudaFuncSetAttribute(snp::k_compress_v1<SNP_HASH_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kCompSmem));
+    c->attrs_set = true;
+    return SNP_OK;
+}
+
+int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    if (!s || !*s) return dflt;
+    if (s[0] == 'v' || s[0] == 'V') s++;
+    return atoi(s);
+}
+
+// ---------------------------------------------------------------- launches --
+
+int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const uint64_t *in_off,
+                      const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off,
+                      const uint32_t *out_cap, uint32_t *out_len, int32_t *status, size_t n) {
+    if (n == 0) return SNP_OK;
+    const int warps = 8;
+    unsigned grid = (unsigned)((n + warps - 1) / warps);
+    snp::k_decompress_v1<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap,
+                                                           out_len, status, n);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SNP_OK;
+}
+
+int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const uint64_t *in_off,
+                    const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap,
+                    uint32_t *out_len, int32_t *status, size_t n, uint32_t hash_mode, int frag_mode) {
+    if (n == 0) return SNP_OK;
+    int rc = ctx_set_attrs(c);
+    if (rc) return rc;
+    size_t ctas = (n + kCompWarps - 1) / kCompWarps;
+    unsigned grid = (unsigned)(ctas < (size_t)c->sm_count ? ctas : (size_t)c->sm_count);
+    if (hash_mode == SNP_HASH_CRC32C)
+        snp::k_compress_v1<SNP_HASH_CRC32C><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
+            in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode);
+    else
+        snp::k_compress_v1<SNP_HASH_MUL><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
+            in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SNP_OK;
+}
+
+// ------------------------------------------- concat of fragment outputs ----
+// The `output = output.Slice(written)` running pointer of TryCompress
+// (SnappyCompressor.cs:76-79) as an exclusive scan + gather.
+
+__global__ void k_frag_scan(const uint32_t *__restrict__ len, const int32_t *__restrict__ status,
+                            uint64_t *__restrict__ off, uint64_t *__restrict__ total_and_bad, size_t n) {
+    __shared__ uint64_t part[1024];
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    size_t per = (n + blockDim.x - 1) / blockDim.x;
+    size_t lo = (size_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    uint64_t sum = 0;
+    for (size_t i = lo; i < hi; i++) {
+        sum += len[i];
+        if (status[i] != SNP_OK) bad = 1;
+    }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (unsigned t = 0; t < blockDim.x; t++) {
+            uint64_t v = part[t];
+            part[t] = run;
+            run += v;
+        }
+        total_and_bad[0] = run;
+        total_and_bad[1] = (uint64_t)bad;
+    }
+    __syncthreads();
+    uint64_t run = part[threadIdx.x];
+    for (size_t i = lo; i < hi; i++) {
+        off[i] = run;
+        run += len[i];
+    }
+}
+
+__global__ void k_frag_gather(const uint8_t *__restrict__ tmp, size_t pitch, const uint32_t *__restrict__ len,
+                              const uint64_t *__restrict__ off, uint8_t *__restrict__ out, size_t n) {
+    for (size_t f = blockIdx.x; f < n; f += gridDim.x) {
+        const uint8_t *s = tmp + f * pitch;
+        uint8_t *d = out + off[f];
+        uint32_t l = len[f];
+        for (uint32_t k = threadIdx.x; k < l; k += blockDim.x) d[k] = s[k];
+    }
+}
+
+// --------------------------------------------------------- host-mode staging --
+
+struct Span {
+    uint64_t lo = 0, hi = 0;
+};
+
+Span span_of(const uint64_t *off, const uint32_t *len, size_t n) {
+    Span s;
+    if (n == 0) return s;
+    s.lo = UINT64_MAX;
+    for (size_t i = 0; i < n; i++) {
+        if (off[i] < s.lo) s.lo = off[i];
+        uint64_t e = off[i] + len[i];
+        if (e > s.hi) s.hi = e;
+    }
+    return s;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct MetaLayout {  // one device allocation holding every per-item array
+    size_t in_off, in_len, out_off, out_cap, out_len, status, bytes;
+    explicit MetaLayout(size_t n) {
+        size_t p = 0;
+        in_off = p, p += align_up(n * 8, 256);
+        out_off = p, p += align_up(n * 8, 256);
+        in_len = p, p += align_up(n * 4, 256);
+        out_cap = p, p += align_up(n * 4, 256);
+        out_len = p, p += align_up(n * 4, 256);
+        status = p, p += align_up(n * 4, 256);
+        bytes = p;
+    }
+};
+
+// Runs one batched op on host buffers: stage in, launch, stage out.  Synchronous.
+int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint64_t *in_off,
+                   const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap,
+                   uint32_t *out_len, int32_t *status, size_t n, uint32_t hash_mode) {
+    if (n == 0) return SNP_OK;
+    cudaStream_t s = c->stream;
+    Span si = span_of(in_off, in_len, n), so = span_of(out_off, out_cap, n);
+    MetaLayout ml(n);
+    int rc;
+    if ((rc = c->d_in.reserve(si.hi - si.lo + 16))) return rc;
+    if ((rc = c->d_out.reserve(so.hi - so.lo + 16))) return rc;
+    if ((rc = c->d_meta.reserve(ml.bytes))) return rc;
+    uint8_t *dm = (uint8_t *)c->d_meta.p;
+
+    std::vector<uint64_t> rel_in(n), rel_out(n);
+    for (size_t i = 0; i < n; i++) rel_in[i] = in_off[i] - si.lo;
+    for (size_t i = 0; i < n; i++) rel_out[i] = out_off[i] - so.lo;
+    CU(cudaMemcpyAsync(dm + ml.in_off, rel_in.data(), n * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dm + ml.out_off, rel_out.data(), n * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dm + ml.in_len, in_len, n * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dm + ml.out_cap, out_cap, n * 4, cudaMemcpyHostToDevice, s));
+    if (si.hi > si.lo)
+        CU(cudaMemcpyAsync(c->d_in.p, in_base + si.lo, si.hi - si.lo, cudaMemcpyHostToDevice, s));
+
+    auto *d_in_off = (const uint64_t *)(dm + ml.in_off);
+    auto *d_out_off = (const uint64_t *)(dm + ml.out_off);
+    auto *d_in_len = (const uint32_t *)(dm + ml.in_len);
+    auto *d_out_cap = (const uint32_t *)(dm + ml.out_cap);
+    auto *d_out_len = (uint32_t *)(dm + ml.out_len);
+    auto *d_status = (int32_t *)(dm + ml.status);
+    if (compress)
+        rc = launch_compress(c, s, (const uint8_t *)c->d_in.p, d_in_off, d_in_len, (uint8_t *)c->d_out.p,
+                             d_out_off, d_out_cap, d_out_len, d_status, n, hash_mode, 0);
+    else
+        rc = launch_decompress(c, s, (const uint8_t *)c->d_in.p, d_in_off, d_in_len, (uint8_t *)c->d_out.p,
+                               d_out_off, d_out_cap, d_out_len, d_status, n);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_len, d_out_len, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+
+    // Copy results back in runs of adjacent item regions, so that nothing outside
+    // the callers' capacity regions is ever written.
+    size_t i = 0;
+    while (i < n) {
+        size_t j = i;
+        while (j + 1 < n && out_off[j + 1] == out_off[j] + out_cap[j]) j++;
+        uint64_t lo = out_off[i], hi = out_off[j] + out_len[j];
+        if (hi > lo)
+            CU(cudaMemcpyAsync(out_base + lo, (const uint8_t *)c->d_out.p + (lo - so.lo), hi - lo,
+                               cudaMemcpyDeviceToHost, s));
+        i = j + 1;
+    }
+    CU(cudaStreamSynchronize(s));
+    return SNP_OK;
+}
+
+thread_local std::unique_ptr<snp_ctx, void (*)(snp_ctx *)> g_default_ctx(nullptr, snp_destroy);
+
+int default_ctx(snp_ctx **out) {
+    if (!g_default_ctx) {
+        int dev = 0;
+        int cnt = 0;
+        cudaError_t e = cudaGetDeviceCount(&cnt);
+        if (e != cudaSuccess || cnt == 0) {
+            cuda_fail(e == cudaSuccess ? cudaErrorNoDevice : e, "cudaGetDeviceCount", __LINE__);
+            return SNP_E_NO_DEVICE;
+        }
+        CU(cudaGetDevice(&dev));
+        snp_ctx *c = nullptr;
+        int rc = snp_create(dev, &c);
+        if (rc) return rc;
+        g_default_ctx.reset(c);
+    }
+    *out = g_default_ctx.get();
+    return SNP_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+bool overlaps(const void *a, size_t na, const void *b, size_t nb) {
+    uintptr_t a0 = (uintptr_t)a, b0 = (uintptr_t)b;
+    return na && nb && a0 < b0 + nb && b0 < a0 + na;
+}
+
+int host_varint_read(const uint8_t *in, size_t n, uint32_t *v, int *used) {
+    // VarIntEncoding.Read.cs:38-79
+    uint32_t result = 0;
+    int shift = 0;
+    *v = 0;
+    *used = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t c = in[i], val = c & 0x7f;
+        if (val & ~(0xffffffffu >> shift)) return SNP_INVALID_LENGTH;
+        result |= val << shift;
+        shift += 7;
+        if (c < 128) {
+            *v = result;
+            *used = (int)i + 1;
+            return SNP_OK;
+        }
+        if (shift >= 32) return SNP_INVALID_LENGTH;
+    }
+    return SNP_INCOMPLETE;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI ----
+
+extern "C" {
+
+int snp_abi_version(void) { return SNP_ABI_VERSION; }
+
+const char *snp_status_string(int st) {
+    switch (st) {
+        case SNP_OK: return "OK";
+        case SNP_OUTPUT_TOO_SMALL: return "Output buffer is too small.";
+        case SNP_INVALID_LENGTH: return "Invalid stream length";
+        case SNP_INCOMPLETE: return "Incomplete Snappy block.";
+        case SNP_INVALID_COPY_OFFSET: return "Invalid copy offset";
+        case SNP_DATA_TOO_LONG: return "Data too long";
+        case SNP_E_CUDA: return "CUDA error";
+        case SNP_E_INVALID_ARG: return "invalid argument";
+        case SNP_E_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        case SNP_E_OVERLAP: return "Input and output spans must not overlap.";
+        default: return "unknown status";
+    }
+}
+
+const char *snp_last_error(void) { return g_last_error.c_str(); }
+
+int32_t snp_max_compressed_length(int32_t n) { return 32 + n + n / 6 + 1; }
+int32_t snp_get_max_compressed_length(int32_t n) { return snp_max_compressed_length(n) + 5; }
+
+int snp_uncompressed_length(const uint8_t *in, size_t n, uint32_t *len) {
+    if (!len || (!in && n)) return SNP_E_INVALID_ARG;
+    int used;
+    int st = host_varint_read(in, n, len, &used);
+    if (st != SNP_OK || *len > 0x7fffffffu) {
+        *len = 0;
+        return SNP_INVALID_LENGTH;
+    }
+    return SNP_OK;
+}
+
+int snp_create(int device, snp_ctx **out) {
+    if (!out) return SNP_E_INVALID_ARG;
+    *out = nullptr;
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cuda_fail(e == cudaSuccess ? cudaErrorNoDevice : e, "cudaGetDeviceCount", __LINE__);
+        return SNP_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= cnt) return SNP_E_INVALID_ARG;
+    DeviceGuard g(device);
+    std::unique_ptr<snp_ctx> c(new snp_ctx);
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        g_last_error = "snappier_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                       std::to_string(prop.minor);
+        return SNP_E_NO_DEVICE;
+    }
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 1);
+    c->comp_kernel = env_int("SNP_COMP_KERNEL", 1);
+    *out = c.release();
+    return SNP_OK;
+}
+
+void snp_destroy(snp_ctx *c) {
+    if (!c) return;
+    DeviceGuard g(c->device);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    delete c;  // DevBuf destructors free the scratch on c->device
+}
+
+int snp_ctx_device(const snp_ctx *c) { return c ? c->device : -1; }
+uint64_t snp_ctx_launch_count(const snp_ctx *c) { return c ? c->launches.load() : 0; }
+
+int snp_compress_batch(snp_ctx *c, const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
+                       uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
+                       int32_t *status, size_t n, uint32_t hash_mode, int mem_kind, void *stream) {
+    if (hash_mode > SNP_HASH_MUL || (mem_kind != SNP_MEM_HOST && mem_kind != SNP_MEM_DEVICE))
+        return SNP_E_INVALID_ARG;
+    if (n && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status || !out_base))
+        return SNP_E_INVALID_ARG;
+    int rc;
+    if (!c && (rc = default_ctx(&c))) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    if (mem_kind == SNP_MEM_DEVICE)
+        return launch_compress(c, stream ? (cudaStream_t)stream : c->stream, in_base, in_off, in_len, out_base,
+                               out_off, out_cap, out_len, status, n, hash_mode, 0);
+    return run_host_batch(c, true, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n,
+                          hash_mode);
+}
+
+int snp_decompress_batch(snp_ctx *c, const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
+                         uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
+                         int32_t *status, size_t n, int mem_kind, void *stream) {
+    if (mem_kind != SNP_MEM_HOST && mem_kind != SNP_MEM_DEVICE) return SNP_E_INVALID_ARG;
+    if (n && (!in_base || !in_off || !in_len || !out_off || !out_cap || !out_len || !status))
+        return SNP_E_INVALID_ARG;
+    int rc;
+    if (!c && (rc = default_ctx(&c))) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    if (mem_kind == SNP_MEM_DEVICE)
+        return launch_decompress(c, stream ? (cudaStream_t)stream : c->stream, in_base, in_off, in_len,
+                                 out_base, out_off, out_cap, out_len, status, n);
+    return run_host_batch(c, false, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, 0);
+}
+
+int snp_uncompressed_length_batch(snp_ctx *c, const uint8_t *in_base, const uint64_t *in_off,
+                                  const uint32_t *in_len, uint32_t *ulen, int32_t *status, size_t n,
+                                  int mem_kind, void *stream) {
+    if (mem_kind != SNP_MEM_HOST && mem_kind != SNP_MEM_DEVICE) return SNP_E_INVALID_ARG;
+    if (n && (!in_base || !in_off || !in_len || !ulen || !status)) return SNP_E_INVALID_ARG;
+    if (n == 0) return SNP_OK;
+    if (mem_kind == SNP_MEM_HOST) {
+        // 1..5 bytes per item: not worth a PCIe round trip (same host varint the
+        // single-call path uses).
+        for (size_t i = 0; i < n; i++) status[i] = snp_uncompressed_length(in_base + in_off[i], in_len[i], &ulen[i]);
+        return SNP_OK;
+    }
+    int rc;
+    if (!c && (rc = default_ctx(&c))) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    snp::k_uncompressed_length<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in_base, in_off, in_len, ulen, status, n);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SNP_OK;
+}
+
+int snp_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written, uint32_t hash_mode) {
+    if (!written || (!in && n) || (!out && cap) || hash_mode > SNP_HASH_MUL || n > 0xffffffffull)
+        return SNP_E_INVALID_ARG;
+    *written = 0;
+    if (overlaps(in, n, out, cap)) return SNP_E_OVERLAP;  // SnappyCompressor.cs:27-30
+    if (cap == 0) return SNP_OUTPUT_TOO_SMALL;            // Snappy.cs:57-62
+    snp_ctx *c;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    cudaStream_t s = c->stream;
+
+    if (n <= SNP_BLOCK_SIZE) {  // one fragment: varint + fragment by one warp
+        uint64_t zero = 0;
+        uint32_t in_len = (uint32_t)n, out_len = 0;
+        uint32_t need = (uint32_t)snp_get_max_compressed_length((int32_t)n);
+        uint32_t out_cap = cap < need ? (uint32_t)cap : need;
+        int32_t st = 0;
+        rc = run_host_batch(c, true, in, &zero, &in_len, out, &zero, &out_cap, &out_len, &st, 1, hash_mode);
+        if (rc) return rc;
+        *written = st == SNP_OK ? out_len : 0;
+        return st;
+    }
+
+    // SnappyCompressor.cs:40-80: independent 64 KiB fragments, then concatenation.
+    const size_t nfrag = (n + SNP_BLOCK_SIZE - 1) / SNP_BLOCK_SIZE;
+    const size_t pitch = (size_t)snp_max_compressed_length(SNP_BLOCK_SIZE) + 5;  // 76496, 16-byte multiple
+    // Snappy's varint header, encoded on the host (VarIntEncoding.Write.cs:5-79).
+    uint8_t hdr[5];
+    size_t hdr_len = 0;
+    {
+        uint32_t v = (uint32_t)n;
+        while (v >= 0x80) hdr[hdr_len++] = (uint8_t)(v | 0x80), v >>= 7;
+        hdr[hdr_len++] = (uint8_t)v;
+    }
+    if (cap < hdr_len) return SNP_OUTPUT_TOO_SMALL;
+    MetaLayout ml(nfrag);
+    const size_t scan_bytes = align_up(nfrag * 8, 256) + 256;
+    if ((rc = c->d_in.reserve(n + 16))) return rc;
+    if ((rc = c->d_tmp.reserve(nfrag * pitch))) return rc;
+    if ((rc = c->d_meta.reserve(ml.bytes + scan_bytes))) return rc;
+    uint8_t *dm = (uint8_t *)c->d_meta.p;
+    std::vector<uint64_t> off(nfrag), slot(nfrag);
+    std::vector<uint32_t> len(nfrag), capv(nfrag, (uint32_t)pitch);
+    for (size_t f = 0; f < nfrag; f++) {
+        off[f] = f * (uint64_t)SNP_BLOCK_SIZE;
+        slot[f] = f * pitch;
+        len[f] = (uint32_t)(n - off[f] < SNP_BLOCK_SIZE ? n - off[f] : SNP_BLOCK_SIZE);
+    }
+    CU(cudaMemcpyAsync(dm + ml.in_off, off.data(), nfrag * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dm + ml.out_off, slot.data(), nfrag * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dm + ml.in_len, len.data(), nfrag * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dm + ml.out_cap, capv.data(), nfrag * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, s));
+    auto *d_len = (uint32_t *)(dm + ml.out_len);
+    auto *d_status = (int32_t *)(dm + ml.status);
+    auto *d_scan = (uint64_t *)(dm + ml.bytes);
+    auto *d_total = (uint64_t *)(dm + ml.bytes + align_up(nfrag * 8, 256));
+    rc = launch_compress(c, s, (const uint8_t *)c->d_in.p, (const uint64_t *)(dm + ml.in_off),
+                         (const uint32_t *)(dm + ml.in_len), (uint8_t *)c->d_tmp.p,
+                         (const uint64_t *)(dm + ml.out_off), (const uint32_t *)(dm + ml.out_cap), d_len, d_status,
+                         nfrag, hash_mode, 1);
+    if (rc) return rc;
+    k_frag_scan<<<1, 1024, 0, s>>>(d_len, d_status, d_scan, d_total, nfrag);
+    c->launches++;
+    uint64_t total_bad[2];
+    CU(cudaMemcpyAsync(total_bad, d_total, 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (total_bad[1]) {
+        g_last_error = "internal: fragment compress reported a non-OK status";
+        return SNP_E_CUDA;
+    }
+    size_t total = hdr_len + (size_t)total_bad[0];
+    if (total > cap) return SNP_OUTPUT_TOO_SMALL;  // SnappyCompressor.cs:63-68 (bytesWritten = 0)
+    if ((rc = c->d_out.reserve(total_bad[0] + 16))) return rc;
+    unsigned grid = (unsigned)(nfrag < 4096 ? nfrag : 4096);
+    k_frag_gather<<<grid, 256, 0, s>>>((const uint8_t *)c->d_tmp.p, pitch, d_len, d_scan, (uint8_t *)c->d_out.p,
+                                       nfrag);
+    c->launches++;
+    CU(cudaGetLastError());
+    memcpy(out, hdr, hdr_len);
+    CU(cudaMemcpyAsync(out + hdr_len, c->d_out.p, total_bad[0], cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *written = total;
+    return SNP_OK;
+}
+
+int snp_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written) {
+    if (!written || (!in && n) || (!out && cap) || n > 0xffffffffull) return SNP_E_INVALID_ARG;
+    *written = 0;
+    uint32_t U;
+    int used;
+    int st = host_varint_read(in, n, &U, &used);  // SnappyDecompressor.cs:50-63
+    if (st == SNP_INCOMPLETE) return SNP_INCOMPLETE;
+    if (st != SNP_OK || U > 0x7fffffffu) return SNP_INVALID_LENGTH;
+    snp_ctx *c;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    uint64_t zero = 0;
+    uint32_t in_len = (uint32_t)n, out_len = 0, out_cap = U;
+    int32_t bst = 0;
+    if (cap >= U) {
+        rc = run_host_batch(c, false, in, &zero, &in_len, out, &zero, &out_cap, &out_len, &bst, 1, 0);
+        if (rc) return rc;
+        *written = bst == SNP_OK ? out_len : 0;
+        return bst;
+    }
+    // Caller's buffer is smaller than the declared length.  The reference still
+    // decodes the whole block into its own buffer first, so data errors win over
+    // "too small", and Read() then hands back the first `cap` bytes
+    // (Snappy.cs:172-186, SnappyDecompressor.cs:613-629).
+    std::vector<uint8_t> full(U ? U : 1);
+    rc = run_host_batch(c, false, in, &zero, &in_len, full.data(), &zero, &out_cap, &out_len, &bst, 1, 0);
+    if (rc) return rc;
+    if (bst != SNP_OK) return bst;
+    memcpy(out, full.data(), cap);
+    *written = cap;
+    return SNP_OUTPUT_TOO_SMALL;
+}
+
+}  // extern "C"

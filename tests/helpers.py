@@ -1,0 +1,104 @@
+"""Shared test helpers: committed fixtures (tests/golden/) and seeded input generators."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CORPUS = ["alice29.txt", "asyoulik.txt", "fireworks.jpeg", "geo.protodata", "html", "html_x_4",
+          "kppkn.gtb", "lcet10.txt", "paper-100k.pdf", "plrabn12.txt", "urls.10K"]
+
+
+def load_fixtures() -> dict[str, bytes]:
+    z = np.load(os.path.join(GOLDEN, "reference_fixtures.npz"))
+    return {k: z[k].tobytes() for k in z.files}
+
+
+def load_kats() -> dict:
+    return json.load(open(os.path.join(GOLDEN, "kats.json")))
+
+
+def load_digests() -> dict:
+    return json.load(open(os.path.join(GOLDEN, "oracle_digests.json")))
+
+
+def parse_framed(stream: bytes):
+    """Snappy framing format -> [(chunk_type, body)] (SnappyStreamDecompressor.cs:215-254)."""
+    out, i = [], 0
+    while i < len(stream):
+        t = stream[i]
+        n = int.from_bytes(stream[i + 1:i + 4], "little")
+        out.append((t, stream[i + 4:i + 4 + n]))
+        i += 4 + n
+    return out
+
+
+def golden_blocks(fx: dict[str, bytes]):
+    """The 10 raw Snappy blocks inside the two framed goldens -> [(name, masked_crc, block bytes)]."""
+    res = []
+    for name in ("html_x_4", "alice29"):
+        k = 0
+        for t, body in parse_framed(fx[f"framed/{name}.snappy"]):
+            if t == 0x00:
+                res.append((f"{name}[{k}]", int.from_bytes(body[:4], "little"), body[4:]))
+                k += 1
+    return res
+
+
+def edge_strings(kats: dict) -> list[bytes]:
+    return [(p + f * n + s).encode() for p, f, n, s in kats["edge_strings"]]
+
+
+def blocks_of(data: bytes, size: int = 65536) -> list[bytes]:
+    return [data[i:i + size] for i in range(0, len(data), size)]
+
+
+def random_data_like_reference(rng: np.random.Generator, n: int) -> bytes:
+    """Distribution of SnappyTests.cs:401-446 `RandomData`: runs of a random byte whose
+    length is skewed small (the .NET System.Random sequence itself is not reproducible)."""
+    out = bytearray()
+    while len(out) < n:
+        run = 1
+        if rng.integers(0, 10) == 0:
+            skew = int(rng.integers(0, 9))
+            run = int(rng.integers(0, 1 << skew)) + 1
+        c = int(rng.integers(0, 256)) if rng.integers(0, 2) else int(rng.integers(0, 4)) + ord("a")
+        out += bytes([c]) * run
+    return bytes(out[:n])
+
+
+def synthetic_blocks(seed: int, count: int, size: int = 65536) -> list[bytes]:
+    """A mix of block classes (text-like, LZ-synthetic, records, runs, random)."""
+    rng = np.random.default_rng(seed)
+    words = [bytes(rng.integers(97, 123, size=int(rng.integers(2, 10)), dtype=np.uint8)) for _ in range(512)]
+    res = []
+    for i in range(count):
+        kind = i % 6
+        if kind == 0:  # incompressible
+            b = rng.integers(0, 256, size=size, dtype=np.uint8).tobytes()
+        elif kind == 1:  # word soup (text-like: many short matches)
+            buf = bytearray()
+            while len(buf) < size:
+                buf += words[int(rng.integers(0, 512))] + b" "
+            b = bytes(buf[:size])
+        elif kind == 2:  # 64 fresh + 64 copied from 4096 back (BASELINE config 3 shape)
+            a = bytearray(rng.integers(0, 256, size=size, dtype=np.uint8).tobytes())
+            for s in range(4096, size, 128):
+                a[s + 64:s + 128] = a[s + 64 - 4096:s + 128 - 4096]
+            b = bytes(a)
+        elif kind == 3:  # fixed-width records with slowly varying fields
+            rec = np.zeros((size // 32 + 1, 32), np.uint8)
+            rec[:, 0:4] = np.arange(rec.shape[0], dtype=np.uint32).view(np.uint8).reshape(-1, 4)
+            rec[:, 4:12] = rng.integers(0, 4, size=(rec.shape[0], 8), dtype=np.uint8)
+            rec[:, 12:] = 0x20
+            b = rec.tobytes()[:size]
+        elif kind == 4:  # runs (pattern replication, overlapping copies)
+            b = random_data_like_reference(rng, size)
+        else:  # short period patterns
+            per = int(rng.integers(1, 40))
+            pat = rng.integers(0, 256, size=per, dtype=np.uint8).tobytes()
+            b = (pat * (size // per + 1))[:size]
+        res.append(b)
+    return res

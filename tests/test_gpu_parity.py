@@ -1,0 +1,241 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the CPU oracle on
+the same inputs -- bit-exact for compressed bytes (both hash modes), decompressed bytes,
+lengths and per-block status.  Nothing here reads /root/reference."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _corpus_blocks(fixtures):
+    blocks, names = [], []
+    for f in H.CORPUS:
+        for i, b in enumerate(H.blocks_of(fixtures["corpus/" + f])):
+            blocks.append(b)
+            names.append(f"{f}[{i}]")
+    return names, blocks
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["crc32c", "mul"])
+def test_compress_corpus_blocks_bit_exact(engine, oracle, fixtures, mode):
+    """Every 64 KiB fragment of the reference's 11 corpus files (SnappyTests.cs:8-20)."""
+    from snappier_b200.batch import compress_many
+    names, blocks = _corpus_blocks(fixtures)
+    got, status = compress_many(engine, blocks, mode)
+    assert not status.any()
+    for name, b, g in zip(names, blocks, got):
+        st, want = oracle.compress(b, mode)
+        assert g == want, name
+
+
+def test_compress_golden_chunks_mul_hash(engine, oracle, fixtures):
+    """MUL-hash output equals the reference's own golden chunks byte for byte."""
+    from snappier_b200.batch import compress_many, decompress_many
+    gold = H.golden_blocks(fixtures)
+    raw, status = decompress_many(engine, [b for _, _, b in gold])
+    assert not status.any()
+    for (name, crc, blk), r in zip(gold, raw):
+        assert oracle.crc32c_masked(r) == crc, name
+    comp, status = compress_many(engine, raw, 1)
+    assert not status.any()
+    assert comp == [b for _, _, b in gold]
+
+
+def test_decompress_corpus_blocks(engine, oracle, fixtures):
+    from snappier_b200.batch import decompress_many
+    names, blocks = _corpus_blocks(fixtures)
+    for mode in (0, 1):
+        comp = [oracle.compress(b, mode)[1] for b in blocks]
+        got, status = decompress_many(engine, comp)
+        assert not status.any()
+        assert got == blocks
+    pa = pytest.importorskip("pyarrow")
+    codec = pa.Codec("snappy")  # blocks produced by Google's encoder (different tag mix)
+    comp = [codec.compress(b).to_pybytes() for b in blocks]
+    got, status = decompress_many(engine, comp)
+    assert not status.any() and got == blocks
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["crc32c", "mul"])
+def test_synthetic_blocks_round_trip_and_parity(engine, oracle, mode):
+    from snappier_b200.batch import compress_many, decompress_many
+    blocks = H.synthetic_blocks(1234 + mode, 96)
+    # ragged sizes, including the < 15-byte and table-size boundaries (HashTable.cs:57-71)
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 2, 3, 4, 14, 15, 16, 17, 31, 32, 33, 255, 256, 257, 1023, 1024, 1025, 4095, 4096, 4097,
+              16383, 16384, 16385, 65521, 65535):
+        blocks.append(blocks[int(rng.integers(0, 96))][:n])
+    got, status = compress_many(engine, blocks, mode)
+    assert not status.any()
+    want = [oracle.compress(b, mode)[1] for b in blocks]
+    bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    assert not bad, bad[:10]
+    back, status = decompress_many(engine, got)
+    assert not status.any() and back == blocks
+
+
+def test_edge_strings_single_call_api(oracle, kats):
+    """SnappyTests.cs:178-202 through the Snappy facade mirror (multi-fragment inputs included)."""
+    from snappier_b200 import snappy as S
+    for s in H.edge_strings(kats):
+        for mode in (0, 1):
+            c = S.compress_to_array(s, mode)
+            assert c == oracle.compress(s, mode)[1]
+            assert S.decompress_to_array(c) == s
+            assert S.decompress_to_memory(c).tobytes() == s
+
+
+def test_whole_files_single_call_api(oracle, fixtures):
+    """Snappy.Compress of inputs > 64 KiB = varint ++ independent fragments (SnappyCompressor.cs:40-80);
+    digests pinned in tests/golden/oracle_digests.json."""
+    from snappier_b200 import snappy as S
+    dig = H.load_digests()
+    for f in H.CORPUS:
+        d = fixtures["corpus/" + f]
+        for mode, key in ((0, "crc32c"), (1, "mul")):
+            c = S.compress_to_array(d, mode)
+            assert len(c) == dig[f][key]["len"] and hashlib.sha256(c).hexdigest() == dig[f][key]["sha256"], (f, key)
+        assert S.decompress_to_array(c) == d
+
+
+def test_output_sizing_semantics(oracle):
+    """SnappyTests.cs:41-118."""
+    from snappier_b200 import snappy as S
+    rng = np.random.default_rng(3)
+    d = rng.integers(0, 256, size=100000, dtype=np.uint8).tobytes()
+    full = S.get_max_compressed_length(len(d))
+    out = np.zeros(full, np.uint8)
+    n = S.compress(d, out)
+    want = oracle.compress(d)[1]
+    assert out[:n].tobytes() == want
+    out2 = np.zeros(full - 5, np.uint8)
+    assert S.compress(d, out2) == n and out2[:n].tobytes() == want
+    with pytest.raises(S.ArgumentException):
+        S.compress(d, np.zeros(1024, np.uint8))
+    assert S.try_compress(d, np.zeros(1024, np.uint8)) == (False, 0)
+    assert S.try_compress(d, np.zeros(0, np.uint8)) == (False, 0)
+    assert S.try_compress(d, np.zeros(n, np.uint8))[0] is True
+    assert S.try_compress(d, np.zeros(n - 1, np.uint8)) == (False, 0)
+    # single-fragment bounded slot
+    small = d[:5000]
+    k = len(oracle.compress(small)[1])
+    assert S.try_compress(small, np.zeros(k, np.uint8)) == (True, k)
+    assert S.try_compress(small, np.zeros(k - 1, np.uint8)) == (False, 0)
+    # overlap (SnappyTests.cs:204-210)
+    buf = np.zeros(1024, np.uint8)
+    with pytest.raises(S.InvalidOperationException):
+        S.compress(buf, buf[1023:])
+
+
+def test_bad_data_statuses(engine, oracle, fixtures):
+    """SnappyTests.cs:212-331: same status (hence exception type) as the oracle for every bad input."""
+    from snappier_b200 import snappy as S
+    from snappier_b200.batch import decompress_many
+    bad = [fixtures[f"bad/baddata{i}.snappy"] for i in (1, 2, 3)]
+    c = bytearray(oracle.compress(b"making sure we don't crash with corrupted input")[1])
+    c[1] -= 1
+    c[3] += 1
+    bad.append(bytes(c))
+    c = bytearray(oracle.compress(b"A" * 1000)[1])
+    c[0], c[1] = 255, 127
+    bad.append(bytes(c))
+    bad += [b"", b"\x80", b"\xff" * 6, b"\xff\xff\xff\xff\x1f", b"\x05\x10abc", b"\x04\x0cabcd\x01\x00",
+            b"\x08\x0cabcd\x05\x09", b"\x03\x0cabcd", b"\x04\xf0", b"\x0a\x00a\xfe\x01\x00\x00",
+            b"\x40\x00a\xfe\x01\x00", b"\x00garbage", b"\x02\x04ab\x00c"]
+    good = oracle.compress(b"interleaved good block " * 100)[1]
+    items = []
+    for b in bad:
+        items += [b, good]
+    caps = []
+    for b in items:
+        st, n = oracle.uncompressed_length(b)
+        caps.append(min(n, 1 << 20) if st == 0 else 0)
+    got, status = decompress_many(engine, items, caps)
+    for i, b in enumerate(items):
+        st, dec = oracle.decompress(b, cap=caps[i])
+        assert status[i] == st, (i, b[:16], status[i], st)
+        assert got[i] == dec
+    # a corrupt item never poisons its neighbours
+    assert all(got[i] == b"interleaved good block " * 100 for i in range(1, len(items), 2))
+    for b in bad[:4]:
+        with pytest.raises(S.InvalidDataException):
+            S.decompress_to_array(b)
+    with pytest.raises(S.InvalidDataException):
+        S.decompress(bad[4], np.zeros(16383, np.uint8))
+    # too-small output: ArgumentException / TryDecompress false (SnappyTests.cs:212-242)
+    c = S.compress_to_array(b"A" * 100000)
+    with pytest.raises(S.ArgumentException):
+        S.decompress(c, np.zeros(100, np.uint8))
+    out = np.zeros(100, np.uint8)
+    assert S.try_decompress(c, out) == (False, 100) and out.tobytes() == b"A" * 100
+    assert S.decompress_to_array(b"\x00") == b""
+
+
+def test_hypothesis_fuzz_decoder_never_diverges(engine, oracle):
+    """Random byte soup and mutated valid blocks: status and output always equal the oracle's."""
+    from snappier_b200.batch import decompress_many
+    rng = np.random.default_rng(99)
+    items = []
+    base_blocks = [oracle.compress(b)[1] for b in H.synthetic_blocks(77, 12, size=4096)]
+    for i in range(600):
+        b = bytearray(base_blocks[i % len(base_blocks)])
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        if i % 5 == 0:
+            b = b[: int(rng.integers(0, len(b)))]
+        items.append(bytes(b))
+    for i in range(200):
+        n = int(rng.integers(1, 64))
+        items.append(bytes([int(rng.integers(1, 40))]) + rng.integers(0, 256, size=n, dtype=np.uint8).tobytes())
+    caps = []
+    for b in items:
+        st, n = oracle.uncompressed_length(b)
+        caps.append(min(n, 1 << 16) if st == 0 else 0)
+    got, status = decompress_many(engine, items, caps)
+    for i, b in enumerate(items):
+        st, dec = oracle.decompress(b, cap=caps[i])
+        assert status[i] == st, (i, status[i], st)
+        assert got[i] == dec, i
+
+
+def test_device_mode_large_batch_properties(engine, oracle):
+    """Device-resident batch (the throughput path): compress -> decompress round trip over 4096
+    blocks, per-block parity on a sample, and a checksum of checksums over the full batch."""
+    import torch
+    blocks = H.synthetic_blocks(2024, 64)
+    n = 4096
+    dev = torch.device("cuda:0")
+    src = torch.from_numpy(np.frombuffer(b"".join(blocks), np.uint8).copy()).to(dev)
+    idx = torch.arange(n, device=dev, dtype=torch.int64)
+    in_off = (idx % len(blocks)) * 65536
+    in_len = torch.full((n,), 65536, dtype=torch.int32, device=dev)
+    pitch = 76496
+    comp = torch.zeros(n * pitch, dtype=torch.uint8, device=dev)
+    c_off = idx * pitch
+    c_cap = torch.full((n,), pitch, dtype=torch.int32, device=dev)
+    c_len = torch.zeros(n, dtype=torch.int32, device=dev)
+    status = torch.full((n,), -99, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    before = engine.launch_count
+    engine.compress_batch_device(src, in_off, in_len, comp, c_off, c_cap, c_len, status, 0, stream)
+    out = torch.zeros(n * 65536, dtype=torch.uint8, device=dev)
+    o_off = idx * 65536
+    o_cap = torch.full((n,), 65536, dtype=torch.int32, device=dev)
+    o_len = torch.zeros(n, dtype=torch.int32, device=dev)
+    status2 = torch.full((n,), -99, dtype=torch.int32, device=dev)
+    engine.decompress_batch_device(comp, c_off, c_len, out, o_off, o_cap, o_len, status2, stream)
+    torch.cuda.synchronize()
+    assert engine.launch_count - before == 2
+    assert int(status.abs().sum()) == 0 and int(status2.abs().sum()) == 0
+    assert bool((o_len == 65536).all())
+    want_len = np.array([len(oracle.compress(b)[1]) for b in blocks])
+    assert np.array_equal(c_len.cpu().numpy(), want_len[np.arange(n) % len(blocks)])
+    assert torch.equal(out.view(n // len(blocks), -1), src.view(1, -1).expand(n // len(blocks), -1))
+    cl = c_len.cpu().numpy()
+    ch = comp.view(n, pitch)
+    for i in (0, 1, 63, 64, 2047, 4095):
+        assert ch[i, : cl[i]].cpu().numpy().tobytes() == oracle.compress(blocks[i % len(blocks)])[1]
