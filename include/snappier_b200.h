@@ -123,8 +123,8 @@ int snp_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t
  * decompress: each item is a complete block with its own varint header.
  *
  * ctx == NULL uses the calling thread's default context.  `stream` is a
- * cudaStream_t (NULL = the context's own stream); used for SNP_MEM_DEVICE
- * only.  Return: SNP_OK once the work is done (HOST) / enqueued (DEVICE),
+ * cudaStream_t used for SNP_MEM_DEVICE only (NULL = the legacy default stream,
+ * as everywhere in CUDA; the caller orders the work against its own).  Return: SNP_OK once the work is done (HOST) / enqueued (DEVICE),
  * or a negative snp_error.  Per-item failures are NOT a call failure. */
 int snp_compress_batch(snp_ctx *ctx, const uint8_t *in_base, const uint64_t *in_off,
                        const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off,

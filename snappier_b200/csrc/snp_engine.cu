@@ -422,7 +422,7 @@ int snp_compress_batch(snp_ctx *c, const uint8_t *in_base, const uint64_t *in_of
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     if (mem_kind == SNP_MEM_DEVICE)
-        return launch_compress(c, stream ? (cudaStream_t)stream : c->stream, in_base, in_off, in_len, out_base,
+        return launch_compress(c, (cudaStream_t)stream, in_base, in_off, in_len, out_base,
                                out_off, out_cap, out_len, status, n, hash_mode, 0);
     return run_host_batch(c, true, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n,
                           hash_mode);
@@ -439,7 +439,7 @@ int snp_decompress_batch(snp_ctx *c, const uint8_t *in_base, const uint64_t *in_
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     if (mem_kind == SNP_MEM_DEVICE)
-        return launch_decompress(c, stream ? (cudaStream_t)stream : c->stream, in_base, in_off, in_len,
+        return launch_decompress(c, (cudaStream_t)stream, in_base, in_off, in_len,
                                  out_base, out_off, out_cap, out_len, status, n);
     return run_host_batch(c, false, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, 0);
 }
@@ -460,7 +460,7 @@ int snp_uncompressed_length_batch(snp_ctx *c, const uint8_t *in_base, const uint
     if (!c && (rc = default_ctx(&c))) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     snp::k_uncompressed_length<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in_base, in_off, in_len, ulen, status, n);
     c->launches++;
     CU(cudaGetLastError());
