@@ -17,6 +17,7 @@
 #include "snp_common.cuh"
 #include "snp_compress_v1.cuh"
 #include "snp_decompress_v1.cuh"
+#include "snp_decompress_v2.cuh"
 
 namespace {
 
@@ -70,7 +71,7 @@ struct snp_ctx {
     std::mutex mu;
     std::atomic<uint64_t> launches{0};
     int sm_count = 148;
-    int decomp_kernel = 1;  // SNP_DECOMP_KERNEL
+    int decomp_kernel = 2;  // SNP_DECOMP_KERNEL (1 = baseline, 2 = warp-parallel)
     int comp_kernel = 1;    // SNP_COMP_KERNEL
     DevBuf d_in, d_out, d_meta, d_tmp;
     bool attrs_set = false;
@@ -106,8 +107,12 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
     if (n == 0) return SNP_OK;
     const int warps = 8;
     unsigned grid = (unsigned)((n + warps - 1) / warps);
-    snp::k_decompress_v1<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap,
-                                                           out_len, status, n);
+    if (c->decomp_kernel == 1)
+        snp::k_decompress_v1<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
+                                                               out_cap, out_len, status, n);
+    else
+        snp::k_decompress_v2<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
+                                                               out_cap, out_len, status, n);
     c->launches++;
     CU(cudaGetLastError());
     return SNP_OK;
@@ -391,7 +396,7 @@ int snp_create(int device, snp_ctx **out) {
         return SNP_E_NO_DEVICE;
     }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 1);
+    c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 2);
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 1);
     *out = c.release();
     return SNP_OK;

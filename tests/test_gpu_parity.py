@@ -239,3 +239,44 @@ def test_device_mode_large_batch_properties(engine, oracle):
     ch = comp.view(n, pitch)
     for i in (0, 1, 63, 64, 2047, 4095):
         assert ch[i, : cl[i]].cpu().numpy().tobytes() == oracle.compress(blocks[i % len(blocks)])[1]
+
+
+def _engine_with(env: dict):
+    import os
+    from snappier_b200.batch import Engine
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return Engine(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
+    """A/B: the simple v1 kernels (SNP_*_KERNEL=1) and the default kernels give identical bytes
+    and statuses on corpus blocks, synthetic blocks and corrupted blocks."""
+    from snappier_b200.batch import compress_many, decompress_many
+    e1 = _engine_with({"SNP_DECOMP_KERNEL": "1", "SNP_COMP_KERNEL": "1"})
+    e2 = _engine_with({})
+    _, blocks = _corpus_blocks(fixtures)
+    blocks = blocks + H.synthetic_blocks(5150, 48)
+    c1, s1 = compress_many(e1, blocks, 0)
+    c2, s2 = compress_many(e2, blocks, 0)
+    assert c1 == c2 and not s1.any() and not s2.any()
+    rng = np.random.default_rng(17)
+    items = list(c1)
+    for c in c1[:40]:
+        b = bytearray(c)
+        b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        items.append(bytes(b))
+    caps = [min(oracle.uncompressed_length(b)[1], 1 << 17) for b in items]
+    d1, s1 = decompress_many(e1, items, caps)
+    d2, s2 = decompress_many(e2, items, caps)
+    assert np.array_equal(s1, s2) and d1 == d2
+    assert d2[:len(blocks)] == blocks
+    e1.close()
+    e2.close()
