@@ -18,6 +18,7 @@
 #include "snp_compress_v1.cuh"
 #include "snp_decompress_v1.cuh"
 #include "snp_decompress_v2.cuh"
+#include "snp_decompress_v3.cuh"
 
 namespace {
 
@@ -71,9 +72,10 @@ struct snp_ctx {
     std::mutex mu;
     std::atomic<uint64_t> launches{0};
     int sm_count = 148;
-    int decomp_kernel = 2;  // SNP_DECOMP_KERNEL (1 = baseline, 2 = warp-parallel)
+    int decomp_kernel = 3;  // SNP_DECOMP_KERNEL (1 = baseline, 2/3 = warp-parallel)
     int comp_kernel = 1;    // SNP_COMP_KERNEL
     DevBuf d_in, d_out, d_meta, d_tmp;
+    unsigned long long *d_counter = nullptr;  // work counter of the persistent kernels
     bool attrs_set = false;
 };
 
@@ -89,6 +91,13 @@ int ctx_set_attrs(snp_ctx *c) {
     CU(cudaFuncSetAttribute(snp::k_compress_v1<SNP_HASH_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompSmem));
     c->attrs_set = true;
+    return SNP_OK;
+}
+
+// Zeroes the persistent kernels' work counter on stream s (ordered before the launch).
+int ctx_work_counter(snp_ctx *c, cudaStream_t s) {
+    if (!c->d_counter) CU(cudaMalloc((void **)&c->d_counter, 256));
+    CU(cudaMemsetAsync(c->d_counter, 0, 8, s));
     return SNP_OK;
 }
 
@@ -110,9 +119,17 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
     if (c->decomp_kernel == 1)
         snp::k_decompress_v1<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
                                                                out_cap, out_len, status, n);
-    else
+    else if (c->decomp_kernel == 2)
         snp::k_decompress_v2<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
                                                                out_cap, out_len, status, n);
+    else {
+        int rc = ctx_work_counter(c, s);
+        if (rc) return rc;
+        unsigned pgrid = (unsigned)(c->sm_count * 8);
+        if (pgrid > grid) pgrid = grid;
+        snp::k_decompress_v3<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
+                                                                out_cap, out_len, status, n, c->d_counter);
+    }
     c->launches++;
     CU(cudaGetLastError());
     return SNP_OK;
@@ -396,7 +413,7 @@ int snp_create(int device, snp_ctx **out) {
         return SNP_E_NO_DEVICE;
     }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 2);
+    c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 3);
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 1);
     *out = c.release();
     return SNP_OK;
@@ -409,6 +426,7 @@ void snp_destroy(snp_ctx *c) {
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
+    if (c->d_counter) cudaFree(c->d_counter);
     delete c;  // DevBuf destructors free the scratch on c->device
 }
 
