@@ -1,0 +1,115 @@
+// SnappyNative.cs -- the reference-side binding a Snappier maintainer would add to route the
+// block path through libsnappier_b200 (include/snappier_b200.h).  NOT compiled in this
+// repository (no .NET SDK in the image); the identical ABI is exercised by ctypes
+// (snappier_b200/_native.py) and by the C++ facade (include/snappier_b200.hpp).
+//
+// Drop-in points in the reference (paths relative to Snappier/):
+//   Snappy.TryCompress      Snappy.cs:64-66   -> SnappyNative.TryCompress
+//   Snappy.TryDecompress    Snappy.cs:174-185 -> SnappyNative.TryDecompress
+//   Snappy.DecompressToMemory Snappy.cs:225-234 -> rent GetUncompressedLength bytes, TryDecompress
+//   SnappyStreamCompressor.CompressBlock  Internal/SnappyStreamCompressor.cs:206 -> TryCompress
+using System;
+using System.IO;
+using System.Runtime.InteropServices;
+
+namespace Snappier.Internal
+{
+    internal static unsafe partial class SnappyNative
+    {
+        private const string Lib = "snappier_b200";
+
+        internal enum Status
+        {
+            Ok = 0, OutputTooSmall = 1, InvalidLength = 2, Incomplete = 3, InvalidCopyOffset = 4, DataTooLong = 5,
+            CudaError = -1, InvalidArgument = -2, NoDevice = -3, Overlap = -4,
+        }
+
+        internal enum HashMode : uint { Crc32C = 0, Mul = 1 }
+        internal enum MemKind { Host = 0, Device = 1 }
+
+        [LibraryImport(Lib)] private static partial int snp_get_max_compressed_length(int n);
+        [LibraryImport(Lib)] private static partial int snp_uncompressed_length(byte* input, nuint n, uint* len);
+        [LibraryImport(Lib)] private static partial int snp_compress(byte* input, nuint n, byte* output, nuint cap, nuint* written, uint hashMode);
+        [LibraryImport(Lib)] private static partial int snp_decompress(byte* input, nuint n, byte* output, nuint cap, nuint* written);
+        [LibraryImport(Lib)] private static partial int snp_create(int device, IntPtr* ctx);
+        [LibraryImport(Lib)] private static partial void snp_destroy(IntPtr ctx);
+        [LibraryImport(Lib)] private static partial int snp_compress_batch(IntPtr ctx, byte* inBase, ulong* inOff, uint* inLen,
+            byte* outBase, ulong* outOff, uint* outCap, uint* outLen, int* status, nuint nItems, uint hashMode, int memKind, IntPtr stream);
+        [LibraryImport(Lib)] private static partial int snp_decompress_batch(IntPtr ctx, byte* inBase, ulong* inOff, uint* inLen,
+            byte* outBase, ulong* outOff, uint* outCap, uint* outLen, int* status, nuint nItems, int memKind, IntPtr stream);
+        [LibraryImport(Lib)] private static partial IntPtr snp_last_error();
+
+        // The hash Snappier itself would use on this machine (HashTable.cs:103-123), so that the
+        // native path emits the same bytes as the managed path it replaces.
+        internal static HashMode PlatformHashMode =>
+#if NET8_0_OR_GREATER
+            (System.Runtime.Intrinsics.X86.Sse42.IsSupported || System.Runtime.Intrinsics.Arm.Crc32.IsSupported)
+                ? HashMode.Crc32C : HashMode.Mul;
+#else
+            HashMode.Mul;
+#endif
+
+        internal static int GetMaxCompressedLength(int inputLength) => snp_get_max_compressed_length(inputLength);
+
+        // Body of Snappy.TryCompress (Snappy.cs:55-67).
+        internal static bool TryCompress(ReadOnlySpan<byte> input, Span<byte> output, out int bytesWritten)
+        {
+            fixed (byte* pin = input)
+            fixed (byte* pout = output)
+            {
+                nuint written;
+                var st = (Status)snp_compress(pin, (nuint)input.Length, pout, (nuint)output.Length, &written, (uint)PlatformHashMode);
+                bytesWritten = (int)written;
+                if (st == Status.OutputTooSmall) return false;
+                ThrowFor(st, decompress: false);
+                return true;
+            }
+        }
+
+        // Body of Snappy.GetUncompressedLength (Snappy.cs:142-143).
+        internal static int GetUncompressedLength(ReadOnlySpan<byte> input)
+        {
+            fixed (byte* pin = input)
+            {
+                uint len;
+                if (snp_uncompressed_length(pin, (nuint)input.Length, &len) != 0)
+                    ThrowHelper.ThrowInvalidDataException("Invalid stream length"); // VarIntEncoding.Read.cs:20
+                return (int)len;
+            }
+        }
+
+        // Body of Snappy.TryDecompress (Snappy.cs:172-186).
+        internal static bool TryDecompress(ReadOnlySpan<byte> input, Span<byte> output, out int bytesWritten)
+        {
+            fixed (byte* pin = input)
+            fixed (byte* pout = output)
+            {
+                nuint written;
+                var st = (Status)snp_decompress(pin, (nuint)input.Length, pout, (nuint)output.Length, &written);
+                bytesWritten = (int)written;
+                if (st == Status.OutputTooSmall) return false;   // decompressor.EndOfFile == false
+                ThrowFor(st, decompress: true);
+                return true;
+            }
+        }
+
+        private static void ThrowFor(Status st, bool decompress)
+        {
+            switch (st)
+            {
+                case Status.Ok: return;
+                case Status.InvalidLength:
+                    if (decompress) ThrowHelper.ThrowInvalidOperationException("Invalid stream length"); // SnappyDecompressor.cs:53-56
+                    ThrowHelper.ThrowInvalidDataException("Invalid stream length");
+                    return;
+                case Status.Incomplete: ThrowHelper.ThrowInvalidDataExceptionIncompleteSnappyBlock(); return; // ThrowHelper.cs:27-28
+                case Status.InvalidCopyOffset: ThrowHelper.ThrowInvalidDataException("Invalid copy offset"); return; // SnappyDecompressor.cs:600
+                case Status.DataTooLong: ThrowHelper.ThrowInvalidDataException("Data too long"); return;             // SnappyDecompressor.cs:572,605
+                case Status.Overlap: ThrowHelper.ThrowInvalidOperationException("Input and output spans must not overlap."); return; // SnappyCompressor.cs:29
+                default:
+                    throw new InvalidOperationException(
+                        $"snappier_b200: {st}: {Marshal.PtrToStringUTF8(snp_last_error())} (there is no CPU fallback)");
+            }
+        }
+    }
+}

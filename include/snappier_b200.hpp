@@ -1,0 +1,162 @@
+// snappier_b200.hpp -- C++ host-side mirror of Snappier's static `Snappy` facade
+// (/root/reference/Snappier/Snappy.cs) above the C ABI of snappier_b200.h.
+//
+// The reference is compiled (managed C#) code and no .NET toolchain exists in this
+// image, so the host side is written in C++: same member names, argument meaning
+// and error behaviour, with .NET exceptions mapped to same-named C++ exceptions.
+// csharp/SnappyNative.cs is the P/Invoke equivalent for a machine that has .NET.
+// Header-only; link with -lsnappier_b200.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "snappier_b200.h"
+
+namespace snappier {
+
+struct ArgumentException : std::invalid_argument {
+    using std::invalid_argument::invalid_argument;
+};
+struct InvalidDataException : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct InvalidOperationException : std::logic_error {
+    using std::logic_error::logic_error;
+};
+struct NativeLibraryException : std::runtime_error {  // no GPU / CUDA failure: there is no CPU fallback
+    using std::runtime_error::runtime_error;
+};
+
+// ReadOnlySpan<byte> / Span<byte>
+struct ReadOnlySpan {
+    const uint8_t *data;
+    size_t size;
+};
+struct Span {
+    uint8_t *data;
+    size_t size;
+};
+
+// IMemoryOwner<byte> returned by CompressToMemory / DecompressToMemory (ByteArrayPoolMemoryOwner.cs)
+class MemoryOwner {
+public:
+    MemoryOwner() = default;
+    MemoryOwner(std::vector<uint8_t> &&buf, size_t len) : buf_(std::move(buf)), len_(len) {}
+    Span Memory() { return {buf_.data(), len_}; }
+    size_t Length() const { return len_; }
+
+private:
+    std::vector<uint8_t> buf_;
+    size_t len_ = 0;
+};
+
+class Snappy {
+public:
+    // Hash variant of the match finder; Snappier on x64/.NET 8+ uses CRC32C (HashTable.cs:109-117).
+    static uint32_t &HashMode() {
+        static uint32_t mode = SNP_HASH_CRC32C;
+        return mode;
+    }
+
+    // Snappy.cs:20-24
+    static int GetMaxCompressedLength(int inputLength) { return snp_get_max_compressed_length(inputLength); }
+
+    // Snappy.cs:55-67
+    static bool TryCompress(ReadOnlySpan input, Span output, int &bytesWritten) {
+        size_t w = 0;
+        int st = snp_compress(input.data, input.size, output.data, output.size, &w, HashMode());
+        bytesWritten = (int)w;
+        if (st == SNP_OUTPUT_TOO_SMALL) return false;
+        Throw(st, /*decompress=*/false);
+        return true;
+    }
+
+    // Snappy.cs:37-45
+    static int Compress(ReadOnlySpan input, Span output) {
+        int n = 0;
+        if (!TryCompress(input, output, n)) throw ArgumentException("Output buffer is too small.");
+        return n;
+    }
+
+    // Snappy.cs:99-113
+    static MemoryOwner CompressToMemory(ReadOnlySpan input) {
+        std::vector<uint8_t> buf((size_t)GetMaxCompressedLength((int)input.size));
+        int n = 0;
+        if (!TryCompress(input, {buf.data(), buf.size()}, n)) throw InvalidOperationException("unreachable");
+        return MemoryOwner(std::move(buf), (size_t)n);
+    }
+
+    // Snappy.cs:123-132
+    static std::vector<uint8_t> CompressToArray(ReadOnlySpan input) {
+        MemoryOwner m = CompressToMemory(input);
+        Span s = m.Memory();
+        return std::vector<uint8_t>(s.data, s.data + s.size);
+    }
+
+    // Snappy.cs:142-143
+    static int GetUncompressedLength(ReadOnlySpan input) {
+        uint32_t len = 0;
+        if (snp_uncompressed_length(input.data, input.size, &len) != SNP_OK)
+            throw InvalidDataException("Invalid stream length");  // VarIntEncoding.Read.cs:20
+        return (int)len;
+    }
+
+    // Snappy.cs:172-186
+    static bool TryDecompress(ReadOnlySpan input, Span output, int &bytesWritten) {
+        size_t w = 0;
+        int st = snp_decompress(input.data, input.size, output.data, output.size, &w);
+        bytesWritten = (int)w;
+        if (st == SNP_OUTPUT_TOO_SMALL) return false;
+        Throw(st, /*decompress=*/true);
+        return true;
+    }
+
+    // Snappy.cs:153-162
+    static int Decompress(ReadOnlySpan input, Span output) {
+        int n = 0;
+        if (!TryDecompress(input, output, n)) throw ArgumentException("Output buffer is too small.");
+        return n;
+    }
+
+    // Snappy.cs:223-235
+    static MemoryOwner DecompressToMemory(ReadOnlySpan input) {
+        uint32_t len = 0;
+        snp_uncompressed_length(input.data, input.size, &len);  // errors surface from Decompress below
+        std::vector<uint8_t> buf(len ? len : 1);
+        int n = 0;
+        TryDecompress(input, {buf.data(), len}, n);
+        return MemoryOwner(std::move(buf), (size_t)n);
+    }
+
+    // Snappy.cs:273-282
+    static std::vector<uint8_t> DecompressToArray(ReadOnlySpan input) {
+        int len = GetUncompressedLength(input);
+        std::vector<uint8_t> out((size_t)len);
+        Decompress(input, {out.data(), out.size()});
+        return out;
+    }
+
+private:
+    static void Throw(int st, bool decompress) {
+        switch (st) {
+            case SNP_OK: return;
+            case SNP_INVALID_LENGTH:
+                if (decompress) throw InvalidOperationException("Invalid stream length");  // SnappyDecompressor.cs:53-56
+                throw InvalidDataException("Invalid stream length");
+            case SNP_INCOMPLETE: throw InvalidDataException("Incomplete Snappy block.");  // ThrowHelper.cs:27-28
+            case SNP_INVALID_COPY_OFFSET: throw InvalidDataException("Invalid copy offset");  // SnappyDecompressor.cs:600
+            case SNP_DATA_TOO_LONG: throw InvalidDataException("Data too long");  // SnappyDecompressor.cs:572,605
+            case SNP_E_OVERLAP:
+                throw InvalidOperationException("Input and output spans must not overlap.");  // SnappyCompressor.cs:29
+            case SNP_E_INVALID_ARG: throw ArgumentException("invalid argument");
+            default:
+                throw NativeLibraryException(std::string(snp_status_string(st)) + ": " + snp_last_error());
+        }
+    }
+};
+
+}  // namespace snappier
