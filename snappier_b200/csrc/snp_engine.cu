@@ -16,6 +16,7 @@
 
 #include "snp_common.cuh"
 #include "snp_compress_v1.cuh"
+#include "snp_compress_v2.cuh"
 #include "snp_decompress_v1.cuh"
 #include "snp_decompress_v2.cuh"
 #include "snp_decompress_v3.cuh"
@@ -73,13 +74,15 @@ struct snp_ctx {
     std::atomic<uint64_t> launches{0};
     int sm_count = 148;
     int decomp_kernel = 3;  // SNP_DECOMP_KERNEL (1 = baseline, 2/3 = warp-parallel)
-    int comp_kernel = 1;    // SNP_COMP_KERNEL
+    int comp_kernel = 2;    // SNP_COMP_KERNEL (1 = baseline, 2 = warp-parallel probes)
     DevBuf d_in, d_out, d_meta, d_tmp;
     unsigned long long *d_counter = nullptr;  // work counter of the persistent kernels
     bool attrs_set = false;
 };
 
 namespace {
+
+int ctx_work_counter(snp_ctx *c, cudaStream_t s);
 
 constexpr int kCompWarps = 7;  // 7 x 32 KiB tables + 2 KiB LUT = 226 KiB <= 227 KiB
 constexpr size_t kCompSmem = (size_t)kCompWarps * 32768 + 2048;
@@ -90,6 +93,13 @@ int ctx_set_attrs(snp_ctx *c) {
                             (int)kCompSmem));
     CU(cudaFuncSetAttribute(snp::k_compress_v1<SNP_HASH_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompSmem));
+    CU(cudaFuncSetAttribute(snp::k_compress_v2<SNP_HASH_CRC32C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kCompSmem));
+    CU(cudaFuncSetAttribute(snp::k_compress_v2<SNP_HASH_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)kCompSmem));
+    snp::k_init_probe_sched<<<1, 32, 0, c->stream>>>();
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
     c->attrs_set = true;
     return SNP_OK;
 }
@@ -143,12 +153,22 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
     if (rc) return rc;
     size_t ctas = (n + kCompWarps - 1) / kCompWarps;
     unsigned grid = (unsigned)(ctas < (size_t)c->sm_count ? ctas : (size_t)c->sm_count);
-    if (hash_mode == SNP_HASH_CRC32C)
-        snp::k_compress_v1<SNP_HASH_CRC32C><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
-            in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode);
-    else
-        snp::k_compress_v1<SNP_HASH_MUL><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
-            in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode);
+    if (c->comp_kernel == 1) {
+        if (hash_mode == SNP_HASH_CRC32C)
+            snp::k_compress_v1<SNP_HASH_CRC32C><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
+                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode);
+        else
+            snp::k_compress_v1<SNP_HASH_MUL><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
+                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode);
+    } else {
+        if ((rc = ctx_work_counter(c, s))) return rc;
+        if (hash_mode == SNP_HASH_CRC32C)
+            snp::k_compress_v2<SNP_HASH_CRC32C><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
+                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, c->d_counter);
+        else
+            snp::k_compress_v2<SNP_HASH_MUL><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
+                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, c->d_counter);
+    }
     c->launches++;
     CU(cudaGetLastError());
     return SNP_OK;
@@ -414,7 +434,7 @@ int snp_create(int device, snp_ctx **out) {
     }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 3);
-    c->comp_kernel = env_int("SNP_COMP_KERNEL", 1);
+    c->comp_kernel = env_int("SNP_COMP_KERNEL", 2);
     *out = c.release();
     return SNP_OK;
 }
