@@ -459,7 +459,8 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("decompress_dram_bytes_per_launch")
+        per_block = json.load(open(tpath)).get("decompress_dram_bytes_per_block")
+        traffic = int(per_block * n) if per_block else None  # ncu --set full capture, scaled to this launch
 
     cpu = None
     if not args.no_cpu_baseline:
