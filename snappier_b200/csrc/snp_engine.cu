@@ -5,6 +5,7 @@
 // only host-side arithmetic is the 1..5-byte varint length prefix, which the
 // reference also reads before it decides how much memory to rent,
 // SnappyDecompressor.cs:110-173).
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -42,6 +43,15 @@ int cuda_fail(cudaError_t e, const char *what, int line) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call, __LINE__); \
     } while (0)
 
+struct PinnedBuf {  // grow-only pinned host staging (metadata only; payloads are the caller's)
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n);
+    ~PinnedBuf() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
 struct DevBuf {  // grow-only device scratch
     void *p = nullptr;
     size_t cap = 0;
@@ -65,6 +75,17 @@ struct DevBuf {  // grow-only device scratch
     }
 };
 
+int PinnedBuf::reserve(size_t n) {
+    if (n <= cap) return SNP_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, n + n / 2 + 4096);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost(meta)", __LINE__);
+    cap = n + n / 2 + 4096;
+    return SNP_OK;
+}
+
 }  // namespace
 
 struct snp_ctx {
@@ -76,13 +97,21 @@ struct snp_ctx {
     int decomp_kernel = 3;  // SNP_DECOMP_KERNEL (1 = baseline, 2/3 = warp-parallel)
     int comp_kernel = 2;    // SNP_COMP_KERNEL (1 = baseline, 2 = warp-parallel probes)
     DevBuf d_in, d_out, d_meta, d_tmp;
-    unsigned long long *d_counter = nullptr;  // work counter of the persistent kernels
+    unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
+    unsigned counter_seq = 0;
+    static constexpr int kSlots = 4;  // host-mode pipeline depth (H2D | kernel | D2H overlap)
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t meta_ready = nullptr;
+        DevBuf d_in, d_out, d_meta;
+        PinnedBuf h_meta;  // same layout as d_meta: async both ways regardless of the caller's arrays
+    } slots[kSlots];
     bool attrs_set = false;
 };
 
 namespace {
 
-int ctx_work_counter(snp_ctx *c, cudaStream_t s);
+int ctx_work_counter(snp_ctx *c, cudaStream_t s, unsigned long long **out);
 
 constexpr int kCompWarps = 7;  // 7 x 32 KiB tables + 2 KiB LUT = 226 KiB <= 227 KiB
 constexpr size_t kCompSmem = (size_t)kCompWarps * 32768 + 2048;
@@ -104,10 +133,15 @@ int ctx_set_attrs(snp_ctx *c) {
     return SNP_OK;
 }
 
-// Zeroes the persistent kernels' work counter on stream s (ordered before the launch).
-int ctx_work_counter(snp_ctx *c, cudaStream_t s) {
-    if (!c->d_counter) CU(cudaMalloc((void **)&c->d_counter, 256));
-    CU(cudaMemsetAsync(c->d_counter, 0, 8, s));
+// Hands out a zeroed work counter for one persistent launch on stream s (the memset is
+// ordered before the launch).  Counters rotate through a pool so that launches in flight
+// on different streams never share one.
+constexpr unsigned kCounterPool = 64;
+int ctx_work_counter(snp_ctx *c, cudaStream_t s, unsigned long long **out) {
+    if (!c->d_counters) CU(cudaMalloc((void **)&c->d_counters, kCounterPool * 32));
+    unsigned long long *p = c->d_counters + 4 * (c->counter_seq++ % kCounterPool);
+    CU(cudaMemsetAsync(p, 0, 8, s));
+    *out = p;
     return SNP_OK;
 }
 
@@ -133,12 +167,13 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
         snp::k_decompress_v2<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
                                                                out_cap, out_len, status, n);
     else {
-        int rc = ctx_work_counter(c, s);
+        unsigned long long *ctr;
+        int rc = ctx_work_counter(c, s, &ctr);
         if (rc) return rc;
         unsigned pgrid = (unsigned)(c->sm_count * 8);
         if (pgrid > grid) pgrid = grid;
         snp::k_decompress_v3<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
-                                                                out_cap, out_len, status, n, c->d_counter);
+                                                                out_cap, out_len, status, n, ctr);
     }
     c->launches++;
     CU(cudaGetLastError());
@@ -161,13 +196,14 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
             snp::k_compress_v1<SNP_HASH_MUL><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
                 in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode);
     } else {
-        if ((rc = ctx_work_counter(c, s))) return rc;
+        unsigned long long *ctr;
+        if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
         if (hash_mode == SNP_HASH_CRC32C)
             snp::k_compress_v2<SNP_HASH_CRC32C><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
-                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, c->d_counter);
+                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr);
         else
             snp::k_compress_v2<SNP_HASH_MUL><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
-                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, c->d_counter);
+                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr);
     }
     c->launches++;
     CU(cudaGetLastError());
@@ -255,30 +291,44 @@ struct MetaLayout {  // one device allocation holding every per-item array
     }
 };
 
-// Runs one batched op on host buffers: stage in, launch, stage out.  Synchronous.
-int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint64_t *in_off,
-                   const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap,
-                   uint32_t *out_len, int32_t *status, size_t n, uint32_t hash_mode) {
-    if (n == 0) return SNP_OK;
-    cudaStream_t s = c->stream;
-    Span si = span_of(in_off, in_len, n), so = span_of(out_off, out_cap, n);
+// Runs one batched op on host buffers.  Synchronous for the caller, but internally the batch is
+// cut into chunks that flow through kSlots streams, so that the H2D copy of chunk k+1, the
+// kernel of chunk k and the D2H copy of chunk k-1 overlap (PCIe is full duplex).  With pinned
+// host buffers the copies are true DMA; with pageable buffers the driver stages them and the
+// overlap degrades gracefully.
+struct Chunk {
+    size_t a = 0, b = 0;  // item range
+    Span si, so;
+    int slot = 0;
+};
+
+int chunk_phase1(snp_ctx *c, const Chunk &ck, bool compress, const uint8_t *in_base, const uint64_t *in_off,
+                 const uint32_t *in_len, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
+                 int32_t *status, uint32_t hash_mode, std::vector<uint64_t> &rel) {
+    snp_ctx::Slot &sl = c->slots[ck.slot];
+    cudaStream_t s = sl.stream;
+    const size_t n = ck.b - ck.a;
     MetaLayout ml(n);
     int rc;
-    if ((rc = c->d_in.reserve(si.hi - si.lo + 16))) return rc;
-    if ((rc = c->d_out.reserve(so.hi - so.lo + 16))) return rc;
-    if ((rc = c->d_meta.reserve(ml.bytes))) return rc;
-    uint8_t *dm = (uint8_t *)c->d_meta.p;
-
-    std::vector<uint64_t> rel_in(n), rel_out(n);
-    for (size_t i = 0; i < n; i++) rel_in[i] = in_off[i] - si.lo;
-    for (size_t i = 0; i < n; i++) rel_out[i] = out_off[i] - so.lo;
-    CU(cudaMemcpyAsync(dm + ml.in_off, rel_in.data(), n * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(dm + ml.out_off, rel_out.data(), n * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(dm + ml.in_len, in_len, n * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(dm + ml.out_cap, out_cap, n * 4, cudaMemcpyHostToDevice, s));
-    if (si.hi > si.lo)
-        CU(cudaMemcpyAsync(c->d_in.p, in_base + si.lo, si.hi - si.lo, cudaMemcpyHostToDevice, s));
-
+    CU(cudaStreamSynchronize(s));  // the slot's previous chunk is completely done
+    if ((rc = sl.d_in.reserve(ck.si.hi - ck.si.lo + 16))) return rc;
+    if ((rc = sl.d_out.reserve(ck.so.hi - ck.so.lo + 16))) return rc;
+    if ((rc = sl.d_meta.reserve(ml.bytes))) return rc;
+    if ((rc = sl.h_meta.reserve(ml.bytes))) return rc;
+    uint8_t *dm = (uint8_t *)sl.d_meta.p;
+    uint8_t *hm = (uint8_t *)sl.h_meta.p;
+    (void)rel;
+    {
+        uint64_t *ri = (uint64_t *)(hm + ml.in_off), *ro = (uint64_t *)(hm + ml.out_off);
+        for (size_t i = 0; i < n; i++) ri[i] = in_off[ck.a + i] - ck.si.lo;
+        for (size_t i = 0; i < n; i++) ro[i] = out_off[ck.a + i] - ck.so.lo;
+        memcpy(hm + ml.in_len, in_len + ck.a, n * 4);
+        memcpy(hm + ml.out_cap, out_cap + ck.a, n * 4);
+    }
+    // in_off .. out_cap are contiguous in the layout: one H2D for all input metadata
+    CU(cudaMemcpyAsync(dm, hm, ml.out_len, cudaMemcpyHostToDevice, s));
+    if (ck.si.hi > ck.si.lo)
+        CU(cudaMemcpyAsync(sl.d_in.p, in_base + ck.si.lo, ck.si.hi - ck.si.lo, cudaMemcpyHostToDevice, s));
     auto *d_in_off = (const uint64_t *)(dm + ml.in_off);
     auto *d_out_off = (const uint64_t *)(dm + ml.out_off);
     auto *d_in_len = (const uint32_t *)(dm + ml.in_len);
@@ -286,30 +336,87 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
     auto *d_out_len = (uint32_t *)(dm + ml.out_len);
     auto *d_status = (int32_t *)(dm + ml.status);
     if (compress)
-        rc = launch_compress(c, s, (const uint8_t *)c->d_in.p, d_in_off, d_in_len, (uint8_t *)c->d_out.p,
-                             d_out_off, d_out_cap, d_out_len, d_status, n, hash_mode, 0);
+        rc = launch_compress(c, s, (const uint8_t *)sl.d_in.p, d_in_off, d_in_len, (uint8_t *)sl.d_out.p, d_out_off,
+                             d_out_cap, d_out_len, d_status, n, hash_mode, 0);
     else
-        rc = launch_decompress(c, s, (const uint8_t *)c->d_in.p, d_in_off, d_in_len, (uint8_t *)c->d_out.p,
+        rc = launch_decompress(c, s, (const uint8_t *)sl.d_in.p, d_in_off, d_in_len, (uint8_t *)sl.d_out.p,
                                d_out_off, d_out_cap, d_out_len, d_status, n);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out_len, d_out_len, n * 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    (void)out_len;
+    (void)status;
+    // out_len + status are contiguous: one D2H into the pinned mirror
+    CU(cudaMemcpyAsync(hm + ml.out_len, dm + ml.out_len, ml.bytes - ml.out_len, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(sl.meta_ready, s));
+    return SNP_OK;
+}
 
-    // Copy results back in runs of adjacent item regions, so that nothing outside
-    // the callers' capacity regions is ever written.
-    size_t i = 0;
-    while (i < n) {
+// Copy a chunk's results back in runs of adjacent item regions, trimmed to the bytes
+// produced, so that nothing outside the callers' capacity regions is ever written.
+int chunk_phase2(snp_ctx *c, const Chunk &ck, uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap,
+                 uint32_t *out_len, int32_t *status) {
+    snp_ctx::Slot &sl = c->slots[ck.slot];
+    CU(cudaEventSynchronize(sl.meta_ready));  // out_len / status of this chunk are on the host now
+    {
+        MetaLayout ml(ck.b - ck.a);
+        const uint8_t *hm = (const uint8_t *)sl.h_meta.p;
+        memcpy(out_len + ck.a, hm + ml.out_len, (ck.b - ck.a) * 4);
+        memcpy(status + ck.a, hm + ml.status, (ck.b - ck.a) * 4);
+    }
+    size_t i = ck.a;
+    while (i < ck.b) {
         size_t j = i;
-        while (j + 1 < n && out_off[j + 1] == out_off[j] + out_cap[j]) j++;
+        while (j + 1 < ck.b && out_off[j + 1] == out_off[j] + out_cap[j]) j++;
         uint64_t lo = out_off[i], hi = out_off[j] + out_len[j];
         if (hi > lo)
-            CU(cudaMemcpyAsync(out_base + lo, (const uint8_t *)c->d_out.p + (lo - so.lo), hi - lo,
-                               cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(out_base + lo, (const uint8_t *)sl.d_out.p + (lo - ck.so.lo), hi - lo,
+                               cudaMemcpyDeviceToHost, sl.stream));
         i = j + 1;
     }
-    CU(cudaStreamSynchronize(s));
     return SNP_OK;
+}
+
+int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint64_t *in_off,
+                   const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap,
+                   uint32_t *out_len, int32_t *status, size_t n, uint32_t hash_mode) {
+    if (n == 0) return SNP_OK;
+    for (auto &sl : c->slots) {
+        if (!sl.stream) CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (!sl.meta_ready) CU(cudaEventCreateWithFlags(&sl.meta_ready, cudaEventDisableTiming));
+    }
+    constexpr uint64_t kChunkBytes = 128ull << 20;  // per-chunk output span target
+    constexpr size_t kChunkItems = 16384;
+    std::vector<uint64_t> rel;
+    Chunk prev;
+    bool have_prev = false;
+    int rc = SNP_OK, k = 0;
+    size_t a = 0;
+    while (a < n && rc == SNP_OK) {
+        Chunk ck;
+        ck.a = a;
+        ck.slot = k++ % snp_ctx::kSlots;
+        uint64_t ilo = UINT64_MAX, ihi = 0, olo = UINT64_MAX, ohi = 0;
+        size_t b = a;
+        while (b < n && b - a < kChunkItems) {
+            uint64_t nilo = std::min(ilo, in_off[b]), nihi = std::max(ihi, in_off[b] + in_len[b]);
+            uint64_t nolo = std::min(olo, out_off[b]), nohi = std::max(ohi, out_off[b] + out_cap[b]);
+            if (b > a && (nohi - nolo > kChunkBytes || nihi - nilo > kChunkBytes)) break;
+            ilo = nilo, ihi = nihi, olo = nolo, ohi = nohi;
+            b++;
+        }
+        ck.b = b;
+        ck.si.lo = ilo, ck.si.hi = ihi, ck.so.lo = olo, ck.so.hi = ohi;
+        rc = chunk_phase1(c, ck, compress, in_base, in_off, in_len, out_off, out_cap, out_len, status, hash_mode, rel);
+        if (rc == SNP_OK && have_prev) rc = chunk_phase2(c, prev, out_base, out_off, out_cap, out_len, status);
+        prev = ck;
+        have_prev = true;
+        a = b;
+    }
+    if (rc == SNP_OK && have_prev) rc = chunk_phase2(c, prev, out_base, out_off, out_cap, out_len, status);
+    for (auto &sl : c->slots) {
+        cudaError_t e = cudaStreamSynchronize(sl.stream);
+        if (e != cudaSuccess && rc == SNP_OK) rc = cuda_fail(e, "cudaStreamSynchronize(slot)", __LINE__);
+    }
+    return rc;
 }
 
 thread_local std::unique_ptr<snp_ctx, void (*)(snp_ctx *)> g_default_ctx(nullptr, snp_destroy);
@@ -446,7 +553,11 @@ void snp_destroy(snp_ctx *c) {
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
-    if (c->d_counter) cudaFree(c->d_counter);
+    if (c->d_counters) cudaFree(c->d_counters);
+    for (auto &sl : c->slots) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream), cudaStreamDestroy(sl.stream);
+        if (sl.meta_ready) cudaEventDestroy(sl.meta_ready);
+    }
     delete c;  // DevBuf destructors free the scratch on c->device
 }
 
