@@ -47,7 +47,7 @@ def load_corpus():
     }
 
 
-def make_blocks(torch, corpus_dev, first_block: int, count: int, dev):
+def make_blocks(torch, corpus_dev, first_block: int, count: int, dev, force_class: int | None = None):
     """'Silesia-mix synthetic' (SURVEY.md 8(d) config 2): deterministic per (first_block, count).
     Classes by block index: text 30 %, markup 25 %, binary 25 % (half kppkn.gtb windows, half
     LZ-synthetic: 32 fresh bytes + a 32-byte match 1..32 KiB back), database-like records 10 %,
@@ -57,6 +57,8 @@ def make_blocks(torch, corpus_dev, first_block: int, count: int, dev):
     g.manual_seed(0x5EED0000 + first_block)
     idx = torch.arange(first_block, first_block + count, device=dev, dtype=torch.int64)
     sel = (idx * 2654435761 >> 7) % 100
+    if force_class is not None:  # diagnostics only (scratch/class_bench.py): every block from one class
+        sel = torch.full_like(sel, force_class)
     out = torch.empty((count, BLOCK), dtype=torch.uint8, device=dev)
 
     def windows(name, rows):

@@ -1,0 +1,360 @@
+// snp_decompress_v4.cuh -- warp-parallel batched Snappy block decompressor (sm_100a) with the
+// compressed input staged through TMA bulk copies.
+//
+// Identical decode algorithm to v3; what changes is where the compressed bytes come from:
+// every warp owns a 2 KiB shared-memory ring (4 x 512 B chunks, one mbarrier each).  One
+// elected lane issues `cp.async.bulk.shared.global` (SASS: UBLKCP) for the 16-byte-aligned
+// interior of each chunk up to ~1 KiB ahead of the parse position and arms the chunk's
+// mbarrier with the byte count (expect_tx); the parse window (2 LDS per lane) and the short
+// literals' source bytes (LDS.U8) then never touch the LSU global path, and HBM latency on
+// the serial tag chain is hidden by the asynchronous prefetch instead of by occupancy.
+// The <=15 unaligned head/tail bytes of a block are copied by lanes (bulk copies need 16-byte
+// alignment and must not read outside the caller's buffer).  Literals >= 32 bytes are copied
+// straight from global memory (coalesced), after which the ring is re-primed at the new
+// position.
+//
+// Same algorithm as v2 (speculative 32-position parse -> tag queue in shared
+// memory -> output-centric rounds with pointer doubling), re-engineered for
+// instruction and L1-wavefront count, which is what bounds this kernel (ncu:
+// profiles/r01_decompress_v2.md):
+//   * LUT fields sit on byte boundaries (PRMT extracts), flags in the sign bits;
+//   * all stream addressing is 32-bit offsets from a 4-byte-aligned base;
+//   * tag starts are found with a next-of-next table: 1 + 8 SHFL + 1 REDUX instead
+//     of up to 16 dependent SHFLs;
+//   * every branch condition that spans a *_sync primitive is a warp vote, so the
+//     compiler emits no divergence guards (BRA.DIV/BSSY) around them.
+//
+// Semantics: /root/reference/Snappier/Internal/SnappyDecompressor.cs:43-92,184-347,
+// 556-611 (one-shot); identical results to v1, v2 and oracle/snappy_oracle.c.
+#pragma once
+#include "snp_common.cuh"
+#include "snp_decompress_v3.cuh"  // tag_lut3_entry, WarpQueue3, SNP_QCAP
+
+namespace snp {
+
+// ---- TMA / mbarrier primitives (PTX; cp.async.bulk needs no tensor map for 1-D copies) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#define SNP_RING_BYTES 1024u
+#define SNP_CHUNK_BYTES 256u
+#define SNP_RING_SLOTS 4u
+#define SNP_RING_GUARD 256u  // bytes behind the parse position that queued short literals may still read
+
+struct __align__(16) InRing {
+    uint8_t data[SNP_RING_BYTES];
+    uint64_t bar[SNP_RING_SLOTS];
+};
+
+__device__ __forceinline__ void copy_long_tag4(const uint8_t *__restrict__ in, uint8_t *out, uint32_t cur,
+                                               uint32_t len, bool is_copy, uint32_t srcw, unsigned lane) {
+    uint8_t *d = out + cur;
+    if (!is_copy) {
+        const uint8_t *s = in + srcw;
+        for (uint32_t k = lane; k < len; k += SNP_WARP) d[k] = s[k];
+    } else {
+        const uint32_t off = srcw;
+        const uint8_t *s = d - off;
+        if (off >= SNP_WARP) {
+            for (uint32_t k0 = 0; k0 < len; k0 += SNP_WARP) {
+                uint32_t k = k0 + lane;
+                if (k < len) d[k] = s[k];
+                if (off < len) __syncwarp();  // chunk j+1 may read what chunk j wrote
+            }
+        } else {
+            for (uint32_t k = lane; k < len; k += SNP_WARP) d[k] = s[k % off];  // pattern fill
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ int decompress_block_v4(const uint8_t *__restrict__ in, uint32_t n_in, uint8_t *out,
+                                                uint32_t cap, uint32_t *written, const uint32_t *lut,
+                                                WarpQueue3 *q, InRing *ring, uint32_t &phases) {
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    *written = 0;
+    uint32_t U, used;
+    int st = varint_read(in, n_in, &U, &used);
+    if (st == SNP_INCOMPLETE) return SNP_INCOMPLETE;
+    if (st != SNP_OK || U > 0x7fffffffu) return SNP_INVALID_LENGTH;
+    if (cap < U) return SNP_OUTPUT_TOO_SMALL;
+    if (U == 0) return SNP_OK;
+
+    // 16-byte-aligned view of the input: stream byte p lives at "aligned offset" skew + p from in16,
+    // and in the ring at (skew + p) & (SNP_RING_BYTES - 1).
+    const uint32_t skew = (uint32_t)((uintptr_t)in & 15);
+    const uint8_t *in16 = in - skew;
+    const uint32_t A = skew + n_in;                       // aligned offsets [skew, A) hold the block
+    const uint32_t n_chunks = (A + SNP_CHUNK_BYTES - 1) / SNP_CHUNK_BYTES;
+    const uint32_t blo = (skew + 15u) & ~15u, bhi = A & ~15u;  // [blo, bhi) may be bulk-copied
+    uint32_t issued = 0, ready = 0;                        // chunks [ready, issued) are in flight
+    uint32_t refill_at = 0;                                // parse position at which the ring must advance next
+    uint32_t landed_end = 0;                               // stream bytes < landed_end are in the ring
+    const uint32_t *ring_w = reinterpret_cast<const uint32_t *>(ring->data);
+
+    auto wait_chunk = [&](uint32_t c) {
+        const uint32_t slot = c & (SNP_RING_SLOTS - 1);
+        uint32_t spins = 0;
+        while (!mbar_try_wait(&ring->bar[slot], (phases >> slot) & 1)) {
+            if (++spins > (1u << 26)) __trap();  // a lost completion must abort, never hang the GPU
+        }
+        phases ^= 1u << slot;
+    };
+    auto issue_chunk = [&](uint32_t c) {
+        const uint32_t slot = c & (SNP_RING_SLOTS - 1);
+        const uint32_t c0 = c * SNP_CHUNK_BYTES, c1 = min(c0 + SNP_CHUNK_BYTES, (A + 15u) & ~15u);
+        const uint32_t b0 = max(c0, blo), b1 = min(c1, bhi);
+        if (lane == 0) {
+            if (b1 > b0) {
+                mbar_arrive_expect_tx(&ring->bar[slot], b1 - b0);
+                tma_load_1d(ring->data + (b0 & (SNP_RING_BYTES - 1)), in16 + b0, b1 - b0, &ring->bar[slot]);
+            } else {
+                mbar_arrive(&ring->bar[slot]);
+            }
+        }
+        // unaligned head [skew, blo) and tail [bhi, A) bytes that fall into this chunk: lane copies
+        {
+            const uint32_t h0 = max(c0, skew), h1 = min(min(c1, blo), A);
+            if (h1 > h0 && h0 + lane < h1) ring->data[(h0 + lane) & (SNP_RING_BYTES - 1)] = in16[h0 + lane];
+            const uint32_t t0 = max(max(c0, bhi), blo), t1 = min(c1, A);
+            if (t1 > t0 && t0 + lane < t1) ring->data[(t0 + lane) & (SNP_RING_BYTES - 1)] = in16[t0 + lane];
+        }
+    };
+    // make the ring hold everything from (position - guard) on, and prefetch as far as the slots allow
+    auto refill = [&](uint32_t pos) {
+        const uint32_t a = skew + pos;
+        const uint32_t keep = (a > SNP_RING_GUARD ? a - SNP_RING_GUARD : 0u) / SNP_CHUNK_BYTES;  // oldest live chunk
+        if (keep > issued) {  // jumped over data that was never needed (long literal): skip it
+            while (ready < issued) wait_chunk(ready++);
+            issued = ready = keep;
+        }
+        while (ready < keep && ready < issued) wait_chunk(ready++);  // a slot is re-armed only after its wait
+        while (issued < n_chunks && issued < keep + SNP_RING_SLOTS) issue_chunk(issued++);
+        __syncwarp();
+        refill_at = (keep + 1) * SNP_CHUNK_BYTES + SNP_RING_GUARD - skew;  // where `keep` next changes
+    };
+    auto ensure = [&](uint32_t pos_end) {  // chunks covering stream bytes < pos_end have landed
+        const uint32_t need = min((skew + pos_end - 1) / SNP_CHUNK_BYTES, n_chunks - 1);
+        while (ready <= need && ready < issued) wait_chunk(ready++);
+        landed_end = ready >= n_chunks ? 0xffffffffu : (ready ? ready * SNP_CHUNK_BYTES - skew : 0u);
+    };
+    auto finish = [&]() {  // nothing may be in flight when the warp moves on to its next block
+        while (ready < issued) wait_chunk(ready++);
+    };
+
+    uint32_t ip = used, op = 0, cur = 0, head = 0, tail = 0;
+    bool stop = false;
+    if (lane == 0) q->dst[0] = 0;
+    __syncwarp();
+
+    // ---- drain the queue while `want` more bytes than `keep` are queued -----------
+    auto drain = [&](uint32_t keep) {
+        while (op - cur > keep) {  // op, cur, keep are warp-uniform by construction
+            const uint32_t e = head + 1 + lane;
+            const bool exists = e <= tail;
+            const uint32_t d = exists ? (q->dst[e & (SNP_QCAP - 1)] & 0x7fffffffu) : 0xffffffffu;
+            const uint32_t b = d - cur - 1;  // tag e starts at output byte cur+1+b
+            const uint32_t rem = __shfl_sync(SNP_FULL, d, 0) - cur;  // bytes left in the head tag
+            if (rem >= SNP_WARP) {  // long tag: cooperative path
+                const uint32_t hd = q->dst[head & (SNP_QCAP - 1)], hs = q->src[head & (SNP_QCAP - 1)];
+                const bool isc = hd >> 31;
+                copy_long_tag4(in, out, cur, rem, isc, isc ? hs : hs + (cur - hd), lane);
+                cur += rem;
+                head += 1;
+                continue;
+            }
+            const bool inr = b < SNP_WARP;
+            const uint32_t M = __reduce_or_sync(SNP_FULL, inr ? (1u << b) : 0u);
+            uint32_t nbytes = min(op - cur, (uint32_t)SNP_WARP);
+            {  // stop in front of the first long tag; it takes the cooperative path next
+                const uint32_t dn = __shfl_down_sync(SNP_FULL, d, 1);
+                const bool lng = inr && lane < 31 && dn != 0xffffffffu && (dn - d >= SNP_WARP);
+                const unsigned lm = __ballot_sync(SNP_FULL, lng);
+                if (lm) nbytes = min(nbytes, 1u + __shfl_sync(SNP_FULL, b, __ffs(lm) - 1));
+            }
+            const bool active = lane < nbytes;
+            const uint32_t idx = (head + __popc(M & lt)) & (SNP_QCAP - 1);
+            const uint32_t tdw = q->dst[idx], tsrc = q->src[idx];
+            const uint32_t mypos = cur + lane;
+            // source: sk 0 = input byte sa, 1 = output byte sa, 2 = byte produced by lane sa this round
+            uint32_t sk, sa;
+            if ((int32_t)tdw >= 0) {
+                sk = 0;
+                sa = tsrc + (mypos - tdw);
+            } else {
+                const uint32_t spos = mypos - tsrc;  // tsrc = offset, validated at parse time
+                const bool internal = spos >= cur;
+                sk = internal ? 2u : 1u;
+                sa = internal ? spos - cur : spos;
+            }
+            while (__any_sync(SNP_FULL, active && sk == 2)) {  // pointer doubling, <= 5 trips
+                const uint32_t nk = __shfl_sync(SNP_FULL, sk, sa);
+                const uint32_t na = __shfl_sync(SNP_FULL, sa, sa);
+                if (sk == 2) {
+                    sk = nk;
+                    sa = na;
+                }
+            }
+            if (active) {
+                uint8_t v8;
+                if (sk == 0) v8 = ring->data[(skew + sa) & (SNP_RING_BYTES - 1)];
+                else v8 = out[sa];
+                out[mypos] = v8;
+            }
+            __syncwarp();
+            head += __popc(M & (0xffffffffu >> (SNP_WARP - nbytes)));
+            cur += nbytes;
+        }
+    };
+
+    while (__any_sync(SNP_FULL, !stop && ip < n_in)) {
+        // ---- PARSE: speculative decode of the tag that would start at ip+lane ------
+        if (ip >= refill_at) refill(ip);           // uniform; true once per 512 input bytes
+        if (ip + 40 > landed_end) ensure(ip + 40);  // likewise
+        const uint32_t pos = ip + lane;
+        const uint32_t bo = skew + pos;
+        const uint32_t wi = bo >> 2;
+        const unsigned sh = (bo & 3) * 8;
+        const uint32_t w0 = ring_w[wi & (SNP_RING_BYTES / 4 - 1)];
+        const uint32_t w1 = ring_w[(wi + 1) & (SNP_RING_BYTES / 4 - 1)];
+        const uint32_t v = __funnelshift_r(w0, w1, sh);
+        const uint32_t trailer = __funnelshift_r(v, w1 >> sh, 8);  // bytes pos+1 .. pos+4
+        const uint32_t ent = lut[v & 0xff];
+        const uint32_t hdr = __byte_perm(ent, 0, 0x4441);
+        const bool is_lit = (int32_t)ent < 0;
+        const uint32_t tval = trailer & __funnelshift_rc(0xffffffffu, 0u, __byte_perm(ent, 0, 0x4442));
+        uint32_t len = ent & 0xff;
+        if (ent & 0x40000000u) len = max(tval + 1, tval);  // trailer-length literal, saturating
+        const uint32_t off = ((ent >> 16) & 0x700u) | tval;  // copies only
+        // against the end of the input (SnappyDecompressor.cs:236-297,464-483)
+        const uint32_t left = max(n_in, pos) - pos;  // bytes from the tag byte to the end (0 if past it)
+        const bool is_end = left < hdr;               // nothing here / truncated tag: parsing stops
+        const uint32_t avail = left - hdr;
+        const bool partial = is_lit && !is_end && len > avail;
+        const uint32_t take = partial ? avail : len;
+        const uint32_t nxt_true = lane + hdr + (is_lit ? take : 0u);
+        const uint32_t n1 = (is_end || partial || nxt_true >= SNP_WARP) ? 63u : nxt_true;
+
+        // ---- tag starts: even-indexed tags by walking next-of-next from lane 0,
+        //      odd-indexed tags are the `next` of an even one.  Lane 31 always holds 63.
+        const uint32_t n2 = __shfl_sync(SNP_FULL, n1, n1);
+        bool even = lane == 0;
+        {
+            uint32_t p = 0;
+#pragma unroll
+            for (int s = 0; s < 8; s++) {  // <= 16 tags fit in 32 bytes
+                p = __shfl_sync(SNP_FULL, n2, p);
+                even |= (p == lane);
+            }
+        }
+        const unsigned starts = __ballot_sync(SNP_FULL, even) |
+                                __reduce_or_sync(SNP_FULL, (even && n1 < SNP_WARP) ? (1u << n1) : 0u);
+        const bool is_start = (starts >> lane) & 1;
+        const bool is_tag = is_start && !is_end && take > 0;
+        const unsigned tags = __ballot_sync(SNP_FULL, is_tag);
+        stop = __any_sync(SNP_FULL, is_start && (is_end || partial));
+        const uint32_t ip_next = ip + __shfl_sync(SNP_FULL, nxt_true, 31 - __clz(starts));
+
+        // ---- output offsets: scan of the tag lengths (all but the last are <= 64) ---
+        const uint32_t x = is_tag ? take : 0u;
+        uint32_t incl = x;
+#pragma unroll
+        for (int dlt = 1; dlt < SNP_WARP; dlt <<= 1) {
+            const uint32_t y = __shfl_up_sync(SNP_FULL, incl, dlt);
+            if (lane >= (unsigned)dlt) incl += y;
+        }
+        const uint32_t dst = op + (incl - x);
+
+        // ---- validation in stream order (SnappyDecompressor.cs:570-573,598-606) ------
+        const bool bad_off = is_tag && !is_lit && (off - 1u >= dst);  // off == 0 || off > dst
+        const bool too_long = is_tag && take > U - dst;
+        const unsigned errs = __ballot_sync(SNP_FULL, bad_off || too_long);
+        if (errs) {
+            const int err = bad_off ? SNP_INVALID_COPY_OFFSET : SNP_DATA_TOO_LONG;
+            finish();
+            return __shfl_sync(SNP_FULL, err, __ffs(errs) - 1);
+        }
+
+        // ---- QUEUE append --------------------------------------------------------------
+        if (is_tag) {
+            const uint32_t slot = (tail + __popc(tags & lt)) & (SNP_QCAP - 1);
+            q->dst[slot] = is_lit ? dst : (dst | 0x80000000u);
+            q->src[slot] = is_lit ? pos + hdr : off;
+        }
+        tail += __popc(tags);
+        op += __shfl_sync(SNP_FULL, incl, 31);
+        if (lane == 0) q->dst[tail & (SNP_QCAP - 1)] = op;  // sentinel
+        __syncwarp();
+        ip = ip_next;
+
+        drain(SNP_WARP - 1);  // keep < 32 bytes (hence < 32 tags) queued
+    }
+    drain(0);
+    finish();
+
+    if (op < U) return SNP_INCOMPLETE;  // Snappy.cs:178-181
+    *written = op;
+    return SNP_OK;
+}
+
+// Persistent launch: one CTA slot per (SM x resident CTA); every warp pulls the next block
+// index from a global counter, so cheap (incompressible) and expensive (text) blocks balance
+// across warps instead of leaving warp slots idle until the slowest warp of a CTA retires.
+__global__ void __launch_bounds__(256, 6)
+k_decompress_v4(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
+                const uint32_t *__restrict__ in_len, uint8_t *out_base,
+                const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
+                uint32_t *__restrict__ out_len, int32_t *__restrict__ status, size_t n_items,
+                unsigned long long *__restrict__ next_item) {
+    __shared__ uint32_t lut[256];
+    __shared__ WarpQueue3 queues[8];
+    __shared__ InRing rings[8];
+    lut[threadIdx.x & 255] = tag_lut3_entry(threadIdx.x & 255);
+    const unsigned lane = lane_id();
+    WarpQueue3 *q = &queues[threadIdx.x / SNP_WARP];
+    InRing *ring = &rings[threadIdx.x / SNP_WARP];
+    if (lane < SNP_RING_SLOTS) mbar_init(&ring->bar[lane], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t phases = 0;  // per-slot mbarrier phase parity, carried across this warp's blocks
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(next_item, 1ull);
+        item = __shfl_sync(SNP_FULL, item, 0);
+        if (item >= n_items) break;
+        uint32_t w = 0;
+        int st = decompress_block_v4(in_base + in_off[item], in_len[item], out_base + out_off[item],
+                                     out_cap[item], &w, lut, q, ring, phases);
+        if (lane == 0) {
+            out_len[item] = w;
+            status[item] = st;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace snp

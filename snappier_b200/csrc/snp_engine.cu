@@ -21,6 +21,7 @@
 #include "snp_decompress_v1.cuh"
 #include "snp_decompress_v2.cuh"
 #include "snp_decompress_v3.cuh"
+#include "snp_decompress_v4.cuh"
 
 namespace {
 
@@ -94,7 +95,8 @@ struct snp_ctx {
     std::mutex mu;
     std::atomic<uint64_t> launches{0};
     int sm_count = 148;
-    int decomp_kernel = 3;  // SNP_DECOMP_KERNEL (1 = baseline, 2/3 = warp-parallel)
+    int decomp_kernel = 3;  // SNP_DECOMP_KERNEL (1 = baseline, 2/3 = warp-parallel, 4 = 3 + TMA-staged input;
+                            // measured 10 % slower than 3 because the kernel is issue-bound)
     int comp_kernel = 2;    // SNP_COMP_KERNEL (1 = baseline, 2 = warp-parallel probes)
     DevBuf d_in, d_out, d_meta, d_tmp;
     unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
@@ -170,10 +172,14 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
         unsigned long long *ctr;
         int rc = ctx_work_counter(c, s, &ctr);
         if (rc) return rc;
-        unsigned pgrid = (unsigned)(c->sm_count * 8);
+        unsigned pgrid = (unsigned)(c->sm_count * (c->decomp_kernel == 3 ? 8 : 6));
         if (pgrid > grid) pgrid = grid;
-        snp::k_decompress_v3<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
-                                                                out_cap, out_len, status, n, ctr);
+        if (c->decomp_kernel == 3)
+            snp::k_decompress_v3<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
+                                                                    out_cap, out_len, status, n, ctr);
+        else
+            snp::k_decompress_v4<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
+                                                                    out_cap, out_len, status, n, ctr);
     }
     c->launches++;
     CU(cudaGetLastError());

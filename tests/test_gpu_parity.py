@@ -262,6 +262,7 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     from snappier_b200.batch import compress_many, decompress_many
     e1 = _engine_with({"SNP_DECOMP_KERNEL": "1", "SNP_COMP_KERNEL": "1"})
     e2 = _engine_with({})
+    e4 = _engine_with({"SNP_DECOMP_KERNEL": "4"})  # TMA-staged input ring
     _, blocks = _corpus_blocks(fixtures)
     blocks = blocks + H.synthetic_blocks(5150, 48)
     c1, s1 = compress_many(e1, blocks, 0)
@@ -278,5 +279,13 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     d2, s2 = decompress_many(e2, items, caps)
     assert np.array_equal(s1, s2) and d1 == d2
     assert d2[:len(blocks)] == blocks
+    d4, s4 = decompress_many(e4, items, caps)
+    assert np.array_equal(s4, s2) and d4 == d2
+    # ragged / tiny / unaligned inputs through the ring's head-tail byte path
+    small = [oracle.compress(b[:n])[1] for b in blocks[:8] for n in (0, 1, 5, 15, 16, 17, 31, 33, 255, 257, 511, 513, 1023, 1500)]
+    d4s, s4s = decompress_many(e4, small)
+    d2s, s2s = decompress_many(e2, small)
+    assert d4s == d2s and not s4s.any()
     e1.close()
     e2.close()
+    e4.close()
