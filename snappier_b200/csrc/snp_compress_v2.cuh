@@ -70,16 +70,36 @@ __device__ __forceinline__ uint32_t find_match_length_v2(const uint8_t *__restri
     }
 }
 
-template <int HASH_MODE>
+// Table accessors.  GLOBAL_TABLE = false: the table is this warp's 32 KiB of shared memory
+// (k_compress_v2, <= 7 blocks in flight per SM).  GLOBAL_TABLE = true: the table is a 32 KiB
+// slice of a device buffer that lives in L2 (k_compress_v3): accesses cost L2 latency instead
+// of shared-memory latency, but occupancy is no longer capped by shared memory, and this
+// kernel is bound by dependent-load latency x resident warps (ncu: 11 % issue utilisation,
+// long_scoreboard, profiles/r01_compress_v2_ncu.md).  .cg = cache in L2 only.
+template <bool GLOBAL_TABLE>
+__device__ __forceinline__ uint32_t tbl_load(const uint16_t *table, uint32_t h) {
+    if (GLOBAL_TABLE) return __ldcg(table + h);
+    return table[h];
+}
+template <bool GLOBAL_TABLE>
+__device__ __forceinline__ void tbl_store(uint16_t *table, uint32_t h, uint32_t v) {
+    if (GLOBAL_TABLE) __stcg(table + h, (uint16_t)v);
+    else table[h] = (uint16_t)v;
+}
+
+template <int HASH_MODE, bool GLOBAL_TABLE = false>
 __device__ __noinline__ void compress_fragment_v2(const uint8_t *__restrict__ in, uint32_t n, OutCursor &o,
-                                                  uint16_t *table, const uint16_t *lut) {
+                                                  uint16_t *table, const uint16_t *lut, const uint32_t *sched) {
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
     const int tsize = table_size_for(n);
     {  // HashTable.cs:52
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *t4 = reinterpret_cast<uint4 *>(table);
-        for (int i = lane; i < tsize / 8; i += SNP_WARP) t4[i] = z;
+        for (int i = lane; i < tsize / 8; i += SNP_WARP) {
+            if (GLOBAL_TABLE) __stcg(t4 + i, z);
+            else t4[i] = z;
+        }
         __syncwarp();
     }
     const uint32_t mask = 2u * (uint32_t)(tsize - 1);
@@ -98,7 +118,7 @@ __device__ __noinline__ void compress_fragment_v2(const uint8_t *__restrict__ in
                 nip = p;
             } else {
                 const uint32_t k = kb + lane - (reprobe ? 1u : 0u);
-                const uint32_t s = g_probe_sched[min(k, (uint32_t)SNP_SCHED_LEN - 1)];
+                const uint32_t s = sched[min(k, (uint32_t)SNP_SCHED_LEN - 1)];
                 p = next_emit + 1 + (s & 0xfffffu);
                 nip = p + (s >> 20);
                 term = nip > ip_limit || k >= SNP_SCHED_LEN;  // :323-327 (checked before the table is touched)
@@ -113,14 +133,14 @@ __device__ __noinline__ void compress_fragment_v2(const uint8_t *__restrict__ in
             const unsigned lower = same & lt;
             const uint32_t from_lane = __shfl_sync(SNP_FULL, p, lower ? 31 - __clz(lower) : lane);
             uint32_t cand = 0;
-            if (is_live) cand = lower ? from_lane : table[h];
+            if (is_live) cand = lower ? from_lane : tbl_load<GLOBAL_TABLE>(table, h);
             const bool hit = is_live && ld_le32(in + cand) == x;
             const unsigned hits = __ballot_sync(SNP_FULL, hit);
             const int f = __ffs(hits) - 1;  // -1: no hit
             // ---- commit table writes of probes 0..f (all live probes if no hit), last writer wins
             const unsigned commit = hits ? (live & (0xffffffffu >> (31 - f))) : live;
             __syncwarp();
-            if (((commit >> lane) & 1) && (same & commit & ~lt & ~(1u << lane)) == 0) table[h] = (uint16_t)p;
+            if (((commit >> lane) & 1) && (same & commit & ~lt & ~(1u << lane)) == 0) tbl_store<GLOBAL_TABLE>(table, h, p);
             __syncwarp();
             if (!hits) {
                 if (terms) break;  // ip = nextEmit; goto emit_remainder (:325-326)
@@ -138,7 +158,7 @@ __device__ __noinline__ void compress_fragment_v2(const uint8_t *__restrict__ in
             next_emit = ip;
             if (ip >= ip_limit) break;  // :381-384
             if (lane == 0)               // :393-394
-                table[table_hash<HASH_MODE>(ld_le32(in + ip - 1), mask, lut) >> 1] = (uint16_t)(ip - 1);
+                tbl_store<GLOBAL_TABLE>(table, table_hash<HASH_MODE>(ld_le32(in + ip - 1), mask, lut) >> 1, ip - 1);
             __syncwarp();
             reprobe = true;
             kb = 0;
@@ -148,7 +168,7 @@ __device__ __noinline__ void compress_fragment_v2(const uint8_t *__restrict__ in
 }
 
 template <int HASH_MODE>
-__global__ void __launch_bounds__(7 * SNP_WARP, 1)
+__global__ void __launch_bounds__(6 * SNP_WARP, 1)
 k_compress_v2(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
               const uint32_t *__restrict__ in_len, uint8_t *out_base,
               const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
@@ -157,7 +177,9 @@ k_compress_v2(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned warps = blockDim.x / SNP_WARP;
     uint16_t *lut = reinterpret_cast<uint16_t *>(smem + (size_t)warps * 32768);
+    uint32_t *sched = reinterpret_cast<uint32_t *>(smem + (size_t)warps * 32768 + 2048);  // probe schedule copy
     if (HASH_MODE == SNP_HASH_CRC32C) build_crc_lut(lut, threadIdx.x, blockDim.x);
+    for (unsigned i = threadIdx.x; i < SNP_SCHED_LEN; i += blockDim.x) sched[i] = g_probe_sched[i];
     __syncthreads();
     const unsigned warp = threadIdx.x / SNP_WARP;
     const unsigned lane = lane_id();
@@ -181,7 +203,55 @@ k_compress_v2(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
                 if ((int)lane < need) o.put(lane, (uint8_t)(lane < 4 ? lo >> (8 * lane) : hi));
                 o.pos = need;
             }
-            if (n > 0) compress_fragment_v2<HASH_MODE>(in, n, o, table, lut);
+            if (n > 0) compress_fragment_v2<HASH_MODE>(in, n, o, table, lut, sched);
+            if (o.pos > o.cap) st = SNP_OUTPUT_TOO_SMALL;  // SnappyCompressor.cs:63-68
+        }
+        if (lane == 0) {
+            out_len[item] = st == SNP_OK ? o.pos : 0;
+            status[item] = st;
+        }
+        __syncwarp();
+    }
+}
+
+// k_compress_v3: same algorithm, hash tables in global memory (one 32 KiB slice per resident
+// warp, `tables` holds gridDim.x * warps of them), so the grid runs at full occupancy.
+template <int HASH_MODE>
+__global__ void __launch_bounds__(256)
+k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
+              const uint32_t *__restrict__ in_len, uint8_t *out_base,
+              const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
+              uint32_t *__restrict__ out_len, int32_t *__restrict__ status, size_t n_items, int frag_mode,
+              unsigned long long *__restrict__ next_item, uint16_t *__restrict__ tables) {
+    __shared__ uint16_t lut[1024];
+    __shared__ uint32_t sched[SNP_SCHED_LEN];
+    if (HASH_MODE == SNP_HASH_CRC32C) build_crc_lut(lut, threadIdx.x, blockDim.x);
+    for (unsigned i = threadIdx.x; i < SNP_SCHED_LEN; i += blockDim.x) sched[i] = g_probe_sched[i];
+    __syncthreads();
+    const unsigned warps = blockDim.x / SNP_WARP;
+    const unsigned warp = threadIdx.x / SNP_WARP;
+    const unsigned lane = lane_id();
+    uint16_t *table = tables + ((size_t)blockIdx.x * warps + warp) * 16384;
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(next_item, 1ull);
+        item = __shfl_sync(SNP_FULL, item, 0);
+        if (item >= n_items) break;
+        const uint8_t *in = in_base + in_off[item];
+        uint32_t n = in_len[item];
+        OutCursor o{out_base + out_off[item], out_cap[item], 0};
+        int st = SNP_OK;
+        if (n > SNP_BLOCK_SIZE) {
+            st = SNP_E_INVALID_ARG;
+        } else {
+            if (!frag_mode) {  // SnappyCompressor.cs:34-38
+                uint32_t lo, hi;
+                int need = varint_encode(n, &lo, &hi);
+                if ((int)lane < need) o.put(lane, (uint8_t)(lane < 4 ? lo >> (8 * lane) : hi));
+                o.pos = need;
+            }
+            if (n > 0) compress_fragment_v2<HASH_MODE, true>(in, n, o, table, lut, sched);
             if (o.pos > o.cap) st = SNP_OUTPUT_TOO_SMALL;  // SnappyCompressor.cs:63-68
         }
         if (lane == 0) {

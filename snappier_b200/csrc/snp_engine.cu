@@ -99,6 +99,8 @@ struct snp_ctx {
                             // measured 10 % slower than 3 because the kernel is issue-bound)
     int comp_kernel = 2;    // SNP_COMP_KERNEL (1 = baseline, 2 = warp-parallel probes)
     DevBuf d_in, d_out, d_meta, d_tmp;
+    DevBuf d_tables;           // k_compress_v3: one 32 KiB hash table per resident warp
+    int comp_ctas_per_sm = 8;  // SNP_COMP_CTAS_PER_SM (x 8 warps)
     unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
     unsigned counter_seq = 0;
     static constexpr int kSlots = 4;  // host-mode pipeline depth (H2D | kernel | D2H overlap)
@@ -117,6 +119,9 @@ int ctx_work_counter(snp_ctx *c, cudaStream_t s, unsigned long long **out);
 
 constexpr int kCompWarps = 7;  // 7 x 32 KiB tables + 2 KiB LUT = 226 KiB <= 227 KiB
 constexpr size_t kCompSmem = (size_t)kCompWarps * 32768 + 2048;
+// v2: 6 warps x 32 KiB tables + 2 KiB CRC LUT + probe schedule; the remaining ~30 KiB stay L1
+constexpr int kComp2Warps = 6;
+constexpr size_t kComp2Smem = (size_t)kComp2Warps * 32768 + 2048 + 4 * SNP_SCHED_LEN;
 
 int ctx_set_attrs(snp_ctx *c) {
     if (c->attrs_set) return SNP_OK;
@@ -125,9 +130,9 @@ int ctx_set_attrs(snp_ctx *c) {
     CU(cudaFuncSetAttribute(snp::k_compress_v1<SNP_HASH_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompSmem));
     CU(cudaFuncSetAttribute(snp::k_compress_v2<SNP_HASH_CRC32C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)kCompSmem));
+                            (int)kComp2Smem));
     CU(cudaFuncSetAttribute(snp::k_compress_v2<SNP_HASH_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)kCompSmem));
+                            (int)kComp2Smem));
     snp::k_init_probe_sched<<<1, 32, 0, c->stream>>>();
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -201,14 +206,33 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
         else
             snp::k_compress_v1<SNP_HASH_MUL><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
                 in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode);
+    } else if (c->comp_kernel >= 3) {
+        // hash tables in global memory (L2): occupancy no longer capped by shared memory
+        unsigned long long *ctr;
+        if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
+        const int wpc = 8;
+        const int cps = c->comp_ctas_per_sm;
+        size_t ctas3 = (n + wpc - 1) / wpc;
+        unsigned grid3 = (unsigned)std::min(ctas3, (size_t)c->sm_count * cps);
+        if ((rc = c->d_tables.reserve((size_t)c->sm_count * cps * wpc * 32768))) return rc;
+        if (hash_mode == SNP_HASH_CRC32C)
+            snp::k_compress_v3<SNP_HASH_CRC32C><<<grid3, wpc * SNP_WARP, 0, s>>>(
+                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr,
+                (uint16_t *)c->d_tables.p);
+        else
+            snp::k_compress_v3<SNP_HASH_MUL><<<grid3, wpc * SNP_WARP, 0, s>>>(
+                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr,
+                (uint16_t *)c->d_tables.p);
     } else {
         unsigned long long *ctr;
         if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
+        size_t ctas2 = (n + kComp2Warps - 1) / kComp2Warps;
+        unsigned grid2 = (unsigned)(ctas2 < (size_t)c->sm_count ? ctas2 : (size_t)c->sm_count);
         if (hash_mode == SNP_HASH_CRC32C)
-            snp::k_compress_v2<SNP_HASH_CRC32C><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
+            snp::k_compress_v2<SNP_HASH_CRC32C><<<grid2, kComp2Warps * SNP_WARP, kComp2Smem, s>>>(
                 in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr);
         else
-            snp::k_compress_v2<SNP_HASH_MUL><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
+            snp::k_compress_v2<SNP_HASH_MUL><<<grid2, kComp2Warps * SNP_WARP, kComp2Smem, s>>>(
                 in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr);
     }
     c->launches++;
@@ -547,7 +571,8 @@ int snp_create(int device, snp_ctx **out) {
     }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 3);
-    c->comp_kernel = env_int("SNP_COMP_KERNEL", 2);
+    c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
+    c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     *out = c.release();
     return SNP_OK;
 }
