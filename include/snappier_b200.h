@@ -40,7 +40,11 @@ enum snp_status {
     /* InvalidDataException("Invalid copy offset") -- SnappyDecompressor.cs:600 */
     SNP_INVALID_COPY_OFFSET = 4,
     /* InvalidDataException("Data too long") -- SnappyDecompressor.cs:572,605 */
-    SNP_DATA_TOO_LONG = 5
+    SNP_DATA_TOO_LONG = 5,
+    /* framing format only: InvalidDataException("Unknown chunk type ..") -- SnappyStreamDecompressor.cs:182-185 */
+    SNP_UNKNOWN_CHUNK_TYPE = 6,
+    /* framing format only: InvalidDataException("Chunk CRC mismatch.") -- SnappyStreamDecompressor.cs:127-131,169-173 */
+    SNP_CRC_MISMATCH = 7
 };
 
 /* ---- call-level errors (< 0) ------------------------------------------ */
@@ -140,6 +144,29 @@ int snp_decompress_batch(snp_ctx *ctx, const uint8_t *in_base, const uint64_t *i
 int snp_uncompressed_length_batch(snp_ctx *ctx, const uint8_t *in_base, const uint64_t *in_off,
                                   const uint32_t *in_len, uint32_t *ulen, int32_t *status,
                                   size_t n_items, int mem_kind, void *stream);
+
+/* ---- framing format (the caller either side of the block path) ----
+ * What `new SnappyStream(s, CompressionMode.Compress)` emits for one Write of the whole buffer
+ * followed by Dispose: stream identifier, then one chunk per 64 KiB
+ * [type 0x00 | 0x01][len24][masked CRC32C of the raw chunk][snappy block | raw bytes]
+ * (SnappyStreamCompressor.cs:15-18,166-261).  Host buffers, synchronous. */
+
+/* 10 + n + 8 * ceil(n / 65536): every chunk falls back to raw when compression does not shrink it. */
+size_t snp_frame_max_compressed_length(size_t n);
+int snp_frame_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written,
+                       uint32_t hash_mode);
+/* Sum of the chunks' uncompressed lengths (host-only header walk).  SNP_INCOMPLETE for a
+ * truncated stream, SNP_UNKNOWN_CHUNK_TYPE for reserved unskippable chunks 0x02..0x7f. */
+int snp_frame_uncompressed_length(const uint8_t *in, size_t n, uint64_t *len);
+/* One-shot equivalent of reading a SnappyStream to the end (SnappyStreamDecompressor.cs:38-208):
+ * skippable chunks (>= 0x80, including the stream identifier, whose content the reference does
+ * not validate) are skipped, every data chunk's CRC is verified.  On error *written = 0 and the
+ * status is that of the first bad chunk in stream order. */
+int snp_frame_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written);
+
+/* Batched Crc32CAlgorithm.Compute (+ ApplyMask when masked != 0), Crc32CAlgorithm.cs:41-44,157-158. */
+int snp_crc32c_batch(snp_ctx *ctx, const uint8_t *base, const uint64_t *off, const uint32_t *len,
+                     uint32_t *crc, size_t n_items, int masked, int mem_kind, void *stream);
 
 #ifdef __cplusplus
 }

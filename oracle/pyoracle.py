@@ -173,3 +173,48 @@ def decompress_batch(in_base: np.ndarray, in_off, in_len, out_base: np.ndarray, 
                                      out_base.ctypes.data, out_off.ctypes.data, out_cap.ctypes.data,
                                      out_len.ctypes.data, status.ctypes.data, n, threads)
     return bad, out_len, status
+
+
+# ---- framing format checker (Python over the C primitives; SnappyStreamCompressor.cs:194-261) ----
+STREAM_ID = bytes([0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59])
+UNKNOWN_CHUNK_TYPE, CRC_MISMATCH = 6, 7
+
+
+def frame_compress(data: bytes, hash_mode: int = HASH_CRC32C) -> bytes:
+    out = bytearray(STREAM_ID)
+    for i in range(0, len(data), BLOCK_SIZE):
+        chunk = data[i:i + BLOCK_SIZE]
+        st, c = compress(chunk, hash_mode)
+        assert st == OK
+        ctype, payload = (0x00, c) if len(c) < len(chunk) else (0x01, chunk)
+        out += bytes([ctype]) + (len(payload) + 4).to_bytes(3, "little") + crc32c_masked(chunk).to_bytes(4, "little") + payload
+    return bytes(out)
+
+
+def frame_decompress(stream: bytes) -> tuple[int, bytes]:
+    out, i = bytearray(), 0
+    while i < len(stream):
+        if len(stream) - i < 4:
+            return INCOMPLETE, b""
+        t, n = stream[i], int.from_bytes(stream[i + 1:i + 4], "little")
+        i += 4
+        if len(stream) - i < n:
+            return INCOMPLETE, b""
+        body = stream[i:i + n]
+        i += n
+        if t in (0, 1):
+            if n < 4:
+                return INCOMPLETE, b""
+            crc = int.from_bytes(body[:4], "little")
+            if t == 0:
+                st, raw = decompress(body[4:])
+                if st != OK:
+                    return st, b""
+            else:
+                raw = body[4:]
+            if crc32c_masked(raw) != crc:
+                return CRC_MISMATCH, b""
+            out += raw
+        elif t < 0x80:
+            return UNKNOWN_CHUNK_TYPE, b""
+    return OK, bytes(out)

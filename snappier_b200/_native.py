@@ -14,6 +14,7 @@ SO_PATH = os.path.join(_PKG, "libsnappier_b200.so")
 
 # enum snp_status / snp_error / snp_hash_mode / snp_mem_kind
 OK, OUTPUT_TOO_SMALL, INVALID_LENGTH, INCOMPLETE, INVALID_COPY_OFFSET, DATA_TOO_LONG = range(6)
+UNKNOWN_CHUNK_TYPE, CRC_MISMATCH = 6, 7  # framing format only
 E_CUDA, E_INVALID_ARG, E_NO_DEVICE, E_OVERLAP = -1, -2, -3, -4
 HASH_CRC32C, HASH_MUL = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -26,6 +27,8 @@ SYMBOLS = [
     "snp_create", "snp_destroy", "snp_ctx_device", "snp_ctx_launch_count",
     "snp_compress", "snp_decompress",
     "snp_compress_batch", "snp_decompress_batch", "snp_uncompressed_length_batch",
+    "snp_frame_max_compressed_length", "snp_frame_compress", "snp_frame_uncompressed_length",
+    "snp_frame_decompress", "snp_crc32c_batch",
 ]
 
 _lib = None
@@ -65,6 +68,12 @@ def lib() -> C.CDLL:
     L.snp_compress_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, u32, C.c_int, vp]
     L.snp_decompress_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, C.c_int, vp]
     L.snp_uncompressed_length_batch.argtypes = [vp, vp, vp, vp, vp, vp, sz, C.c_int, vp]
+    L.snp_frame_max_compressed_length.argtypes = [sz]
+    L.snp_frame_max_compressed_length.restype = sz
+    L.snp_frame_compress.argtypes = [vp, sz, vp, sz, C.POINTER(sz), u32]
+    L.snp_frame_uncompressed_length.argtypes = [vp, sz, C.POINTER(C.c_uint64)]
+    L.snp_frame_decompress.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
+    L.snp_crc32c_batch.argtypes = [vp, vp, vp, vp, vp, sz, C.c_int, C.c_int, vp]
     _lib = L
     return L
 

@@ -191,3 +191,19 @@ def test_batch_driver_matches_single_calls(oracle):
     bad, dlen, status = oracle.decompress_batch(cbase, coff, clen, dout, np.arange(len(blocks), dtype=np.uint64) * 65536,
                                                 np.full(len(blocks), 65536, np.uint32), threads=3)
     assert bad == 0 and dout.tobytes() == b"".join(blocks)
+
+
+def test_framing_checker_reproduces_golden_streams(oracle, fixtures):
+    """The oracle-side framing checker (pyoracle.frame_*) is pinned by the reference's two framed
+    goldens: MUL-hash frame_compress reproduces html_x_4.snappy and alice29.snappy byte for byte
+    (stream identifier, chunk headers, masked CRCs, payloads), and frame_decompress inverts them."""
+    html4 = fixtures["corpus/html_x_4"]
+    alice_crlf = fixtures["corpus/alice29.txt"].replace(b"\n", b"\r\n")
+    for raw, name in ((html4, "html_x_4"), (alice_crlf, "alice29")):
+        gold = fixtures[f"framed/{name}.snappy"]
+        assert oracle.frame_compress(raw, oracle.HASH_MUL) == gold
+        assert oracle.frame_decompress(gold) == (oracle.OK, raw)
+        assert oracle.frame_decompress(oracle.frame_compress(raw, oracle.HASH_CRC32C)) == (oracle.OK, raw)
+    # incompressible chunks fall back to type 0x01 with 8 + len bytes (SnappyStreamCompressorTests.cs:7-46)
+    rnd = np.random.default_rng(1).integers(0, 256, size=256, dtype=np.uint8).tobytes()
+    assert len(oracle.frame_compress(rnd)) == 10 + 8 + 256
