@@ -148,6 +148,7 @@ __device__ __noinline__ int decompress_block_v4(const uint8_t *__restrict__ in, 
     auto refill = [&](uint32_t pos) {
         const uint32_t a = skew + pos;
         const uint32_t keep = (a > SNP_RING_GUARD ? a - SNP_RING_GUARD : 0u) / SNP_CHUNK_BYTES;  // oldest live chunk
+        __syncwarp();  // every lane is done reading the slots that are about to be overwritten
         if (keep > issued) {  // jumped over data that was never needed (long literal): skip it
             while (ready < issued) wait_chunk(ready++);
             issued = ready = keep;
@@ -234,7 +235,9 @@ __device__ __noinline__ int decompress_block_v4(const uint8_t *__restrict__ in, 
     while (__any_sync(SNP_FULL, !stop && ip < n_in)) {
         // ---- PARSE: speculative decode of the tag that would start at ip+lane ------
         if (ip >= refill_at) refill(ip);           // uniform; true once per 512 input bytes
-        if (ip + 40 > landed_end) ensure(ip + 40);  // likewise
+        // the window's tags may start up to ip+31, carry 5 header bytes and (if they go through the
+        // rounds) < 32 literal bytes that drain() reads from the ring: all of it must have landed
+        if (ip + 72 > landed_end) ensure(ip + 72);  // likewise
         const uint32_t pos = ip + lane;
         const uint32_t bo = skew + pos;
         const uint32_t wi = bo >> 2;
