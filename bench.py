@@ -50,7 +50,7 @@ def load_corpus():
 def make_blocks(torch, corpus_dev, first_block: int, count: int, dev, force_class: int | None = None):
     """'Silesia-mix synthetic' (SURVEY.md 8(d) config 2): deterministic per (first_block, count).
     Classes by block index: text 30 %, markup 25 %, binary 25 % (half kppkn.gtb windows, half
-    LZ-synthetic: 32 fresh bytes + a 32-byte match 1..32 KiB back), database-like records 10 %,
+    LZ-synthetic: 32 fresh bytes + a 32-byte true match 1..32 KiB back), database-like records 10 %,
     incompressible 10 % (half jpeg windows, half PRNG).  Corpus windows get one byte per 4 KiB
     XOR-perturbed so that no two blocks are identical."""
     g = torch.Generator(device=dev)
@@ -79,15 +79,18 @@ def make_blocks(torch, corpus_dev, first_block: int, count: int, dev, force_clas
         rows = pick(lo, hi)
         if rows.numel():
             windows(name, rows)
-    rows = pick(67, 80)  # LZ-synthetic
-    if rows.numel():
-        n = rows.numel()
+    rows = pick(67, 80)  # LZ-synthetic: 32 fresh bytes + a 32-byte match 1..32 KiB back, built sequentially
+    if rows.numel():  # so that every match is a true copy of what precedes it (sources start inside a fresh run,
+        n = rows.numel()  # where the reference's probe loop has inserted every position)
         R = torch.randint(0, 256, (n, BLOCK), device=dev, generator=g, dtype=torch.int32).to(torch.uint8)
-        seg = torch.arange(BLOCK // 32, device=dev)
-        back = torch.randint(16, 512, (n, BLOCK // 32), device=dev, generator=g) * 2 + 1  # odd: lands in a fresh segment
-        src_seg = torch.where((seg % 2 == 1) & (seg - back >= 0), seg - back, seg)
-        src = (src_seg.unsqueeze(2) * 32 + torch.arange(32, device=dev)).view(n, BLOCK)
-        out[rows] = R.gather(1, src)
+        nseg = BLOCK // 64
+        back = torch.randint(16, 512, (n, nseg), device=dev, generator=g)       # segments back: 1..32 KiB
+        inner = torch.randint(0, 29, (n, nseg), device=dev, generator=g)        # start inside the fresh run
+        k32 = torch.arange(32, device=dev)
+        for sgm in range(16, nseg):
+            src0 = (sgm - torch.minimum(back[:, sgm], torch.full_like(back[:, sgm], sgm))) * 64 + inner[:, sgm]
+            R[:, sgm * 64 + 32: sgm * 64 + 64] = R.gather(1, src0.unsqueeze(1) + k32)
+        out[rows] = R
     rows = pick(80, 90)  # database-like fixed-width records
     if rows.numel():
         n = rows.numel()
