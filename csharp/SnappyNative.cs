@@ -21,6 +21,7 @@ namespace Snappier.Internal
         internal enum Status
         {
             Ok = 0, OutputTooSmall = 1, InvalidLength = 2, Incomplete = 3, InvalidCopyOffset = 4, DataTooLong = 5,
+            UnknownChunkType = 6, CrcMismatch = 7,
             CudaError = -1, InvalidArgument = -2, NoDevice = -3, Overlap = -4,
         }
 
@@ -38,6 +39,12 @@ namespace Snappier.Internal
         [LibraryImport(Lib)] private static partial int snp_decompress_batch(IntPtr ctx, byte* inBase, ulong* inOff, uint* inLen,
             byte* outBase, ulong* outOff, uint* outCap, uint* outLen, int* status, nuint nItems, int memKind, IntPtr stream);
         [LibraryImport(Lib)] private static partial IntPtr snp_last_error();
+        // framing format (what SnappyStreamCompressor.CompressBlock / SnappyStreamDecompressor do per chunk, batched)
+        [LibraryImport(Lib)] private static partial nuint snp_frame_max_compressed_length(nuint n);
+        [LibraryImport(Lib)] private static partial int snp_frame_compress(byte* input, nuint n, byte* output, nuint cap, nuint* written, uint hashMode);
+        [LibraryImport(Lib)] private static partial int snp_frame_uncompressed_length(byte* input, nuint n, ulong* len);
+        [LibraryImport(Lib)] private static partial int snp_frame_decompress(byte* input, nuint n, byte* output, nuint cap, nuint* written);
+        [LibraryImport(Lib)] private static partial int snp_crc32c_batch(IntPtr ctx, byte* inBase, ulong* off, uint* len, uint* crc, nuint nItems, int masked, int memKind, IntPtr stream);
 
         // The hash Snappier itself would use on this machine (HashTable.cs:103-123), so that the
         // native path emits the same bytes as the managed path it replaces.
@@ -106,6 +113,8 @@ namespace Snappier.Internal
                 case Status.InvalidCopyOffset: ThrowHelper.ThrowInvalidDataException("Invalid copy offset"); return; // SnappyDecompressor.cs:600
                 case Status.DataTooLong: ThrowHelper.ThrowInvalidDataException("Data too long"); return;             // SnappyDecompressor.cs:572,605
                 case Status.Overlap: ThrowHelper.ThrowInvalidOperationException("Input and output spans must not overlap."); return; // SnappyCompressor.cs:29
+                case Status.UnknownChunkType: ThrowHelper.ThrowInvalidDataException("Unknown chunk type"); return;   // SnappyStreamDecompressor.cs:182-185
+                case Status.CrcMismatch: ThrowHelper.ThrowInvalidDataException("Chunk CRC mismatch."); return;       // SnappyStreamDecompressor.cs:127-131
                 default:
                     throw new InvalidOperationException(
                         $"snappier_b200: {st}: {Marshal.PtrToStringUTF8(snp_last_error())} (there is no CPU fallback)");

@@ -140,6 +140,26 @@ public:
         return out;
     }
 
+    // ---- framing format, one-shot (SnappyStream.cs + SnappyStreamCompressor/Decompressor.cs) ----
+    // What `new SnappyStream(s, CompressionMode.Compress)` emits for Write(input) + Dispose.
+    static std::vector<uint8_t> FrameCompress(ReadOnlySpan input) {
+        std::vector<uint8_t> out(snp_frame_max_compressed_length(input.size));
+        size_t w = 0;
+        Throw(snp_frame_compress(input.data, input.size, out.data(), out.size(), &w, HashMode()), false);
+        out.resize(w);
+        return out;
+    }
+    // Reading `new SnappyStream(s, CompressionMode.Decompress)` to the end.
+    static std::vector<uint8_t> FrameDecompress(ReadOnlySpan input) {
+        uint64_t len = 0;
+        Throw(snp_frame_uncompressed_length(input.data, input.size, &len), false);
+        std::vector<uint8_t> out(len ? len : 1);
+        size_t w = 0;
+        Throw(snp_frame_decompress(input.data, input.size, out.data(), len, &w), false);
+        out.resize(w);
+        return out;
+    }
+
 private:
     static void Throw(int st, bool decompress) {
         switch (st) {
@@ -150,6 +170,8 @@ private:
             case SNP_INCOMPLETE: throw InvalidDataException("Incomplete Snappy block.");  // ThrowHelper.cs:27-28
             case SNP_INVALID_COPY_OFFSET: throw InvalidDataException("Invalid copy offset");  // SnappyDecompressor.cs:600
             case SNP_DATA_TOO_LONG: throw InvalidDataException("Data too long");  // SnappyDecompressor.cs:572,605
+            case SNP_UNKNOWN_CHUNK_TYPE: throw InvalidDataException("Unknown chunk type");  // SnappyStreamDecompressor.cs:182-185
+            case SNP_CRC_MISMATCH: throw InvalidDataException("Chunk CRC mismatch.");      // SnappyStreamDecompressor.cs:127-131
             case SNP_E_OVERLAP:
                 throw InvalidOperationException("Input and output spans must not overlap.");  // SnappyCompressor.cs:29
             case SNP_E_INVALID_ARG: throw ArgumentException("invalid argument");

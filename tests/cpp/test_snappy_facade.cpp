@@ -71,6 +71,19 @@ int main(int argc, char **argv) {
         CHECK(throws<InvalidDataException>([&] { Snappy::DecompressToArray(ro(b)); }));
     }
     CHECK(throws<InvalidDataException>([&] { Snappy::GetUncompressedLength({nullptr, 0}); }));
+    // SnappyStreamTests.cs:8-262 shape: framed round trip, golden framed stream, CRC corruption
+    {
+        std::vector<uint8_t> framed = Snappy::FrameCompress(ro(input));
+        CHECK(framed.size() > 10 && framed[0] == 0xff && framed[4] == 's');
+        CHECK(Snappy::FrameDecompress(ro(framed)) == input);
+        std::vector<uint8_t> gold = read_file(dir + "/golden_framed.snappy"), gold_raw = read_file(dir + "/golden_raw.bin");
+        CHECK(!gold.empty() && Snappy::FrameDecompress(ro(gold)) == gold_raw);
+        Snappy::HashMode() = SNP_HASH_MUL;  // the hash Snappier uses off x64/.NET 8+: reproduces the golden bytes
+        CHECK(Snappy::FrameCompress(ro(gold_raw)) == gold);
+        Snappy::HashMode() = SNP_HASH_CRC32C;
+        framed[14] ^= 1;
+        CHECK(throws<InvalidDataException>([&] { Snappy::FrameDecompress(ro(framed)); }));
+    }
     std::printf(failures ? "%d FAILURES\n" : "ALL OK\n", failures);
     return failures != 0;
 }

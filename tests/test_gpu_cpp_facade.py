@@ -32,6 +32,8 @@ def test_cpp_facade_runs_like_reference_tests(tmp_path, oracle, fixtures):
     data = fixtures["corpus/html"] + fixtures["corpus/alice29.txt"][:50000]
     open(tmp_path / "input.bin", "wb").write(data)
     open(tmp_path / "input.snappy", "wb").write(oracle.compress(data)[1])
+    open(tmp_path / "golden_framed.snappy", "wb").write(fixtures["framed/html_x_4.snappy"])
+    open(tmp_path / "golden_raw.bin", "wb").write(fixtures["corpus/html_x_4"])
     for i in (1, 2, 3):
         open(tmp_path / f"baddata{i}.snappy", "wb").write(fixtures[f"bad/baddata{i}.snappy"])
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
