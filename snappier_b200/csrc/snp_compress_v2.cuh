@@ -214,15 +214,108 @@ k_compress_v2(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
     }
 }
 
-// k_compress_v3: same algorithm, hash tables in global memory (one 32 KiB slice per resident
-// warp, `tables` holds gridDim.x * warps of them), so the grid runs at full occupancy.
+// ---- k_compress_v3: same algorithm, hash tables in global memory (L2) ------------------------
+// One slice per resident warp, so the grid runs at full occupancy (the shared-memory kernel is
+// capped at 7 blocks in flight per SM and is bound by dependent-load latency).  Entries are
+// widened to 32 bits: low 16 = position (the reference's ushort), high 16 = a fingerprint of the
+// 4 bytes at that position.  The fingerprint is a pure filter -- equal bytes imply equal
+// fingerprints -- that spares the candidate load (a random DRAM sector) for the ~all probes
+// that cannot match; surviving candidates are still verified against the real bytes.
+__device__ __forceinline__ uint32_t fp16(uint32_t x) { return (x * 0x9E3779B1u) >> 16; }
+
+template <int HASH_MODE>
+__device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in, uint32_t n, OutCursor &o,
+                                                  uint32_t *table, const uint16_t *lut, const uint32_t *sched) {
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const int tsize = table_size_for(n);
+    const uint32_t mask = 2u * (uint32_t)(tsize - 1);
+    uint32_t next_emit = 0;
+    if (n >= 15) {  // Constants.InputMarginBytes, SnappyCompressor.cs:190
+        {  // HashTable.cs:52: "zero" = position 0, whose bytes are in[0..3]
+            const uint32_t e0 = fp16(ld_le32(in)) << 16;
+            uint4 z = make_uint4(e0, e0, e0, e0);
+            uint4 *t4 = reinterpret_cast<uint4 *>(table);
+            for (int i = lane; i < tsize / 4; i += SNP_WARP) __stcg(t4 + i, z);
+            __syncwarp();
+        }
+        const uint32_t ip_limit = n - 15;
+        bool reprobe = false;
+        uint32_t kb = 0;
+        for (;;) {
+            uint32_t p, nip;
+            bool term = false;
+            if (reprobe && lane == 0) {
+                p = next_emit;
+                nip = p;
+            } else {
+                const uint32_t k = kb + lane - (reprobe ? 1u : 0u);
+                const uint32_t s = sched[min(k, (uint32_t)SNP_SCHED_LEN - 1)];
+                p = next_emit + 1 + (s & 0xfffffu);
+                nip = p + (s >> 20);
+                term = nip > ip_limit || k >= SNP_SCHED_LEN;  // :323-327
+            }
+            const unsigned terms = __ballot_sync(SNP_FULL, term);
+            const unsigned live = terms ? ((1u << (__ffs(terms) - 1)) - 1u) : SNP_FULL;
+            const bool is_live = (live >> lane) & 1;
+            const uint32_t x = is_live ? ld_le32(in + p) : 0u;
+            const uint32_t h = is_live ? (table_hash<HASH_MODE>(x, mask, lut) >> 1) : (0x10000u + lane);
+            const unsigned same = __match_any_sync(SNP_FULL, h);
+            const unsigned lower = same & lt;
+            const int src = lower ? 31 - __clz(lower) : (int)lane;
+            const uint32_t p_src = __shfl_sync(SNP_FULL, p, src);
+            const uint32_t x_src = __shfl_sync(SNP_FULL, x, src);
+            uint32_t cand = 0;
+            bool hit = false;
+            if (is_live) {
+                if (lower) {  // an earlier probe of this batch owns the bucket: its bytes are in a register
+                    cand = p_src;
+                    hit = x_src == x;
+                } else {
+                    const uint32_t e = __ldcg(table + h);
+                    cand = e & 0xffffu;
+                    if ((e >> 16) == fp16(x)) hit = ld_le32(in + cand) == x;
+                }
+            }
+            const unsigned hits = __ballot_sync(SNP_FULL, hit);
+            const int f = __ffs(hits) - 1;
+            const unsigned commit = hits ? (live & (0xffffffffu >> (31 - f))) : live;
+            if (((commit >> lane) & 1) && (same & commit & ~lt & ~(1u << lane)) == 0)
+                __stcg(table + h, p | (fp16(x) << 16));
+            __syncwarp();
+            if (!hits) {
+                if (terms) break;
+                kb += reprobe ? 31u : 32u;
+                reprobe = false;
+                continue;
+            }
+            uint32_t ip = __shfl_sync(SNP_FULL, p, f);
+            const uint32_t c = __shfl_sync(SNP_FULL, cand, f);
+            if (ip > next_emit) emit_literal_v1(o, in + next_emit, ip - next_emit, lane);
+            const uint32_t m = 4 + find_match_length_v2(in, c + 4, ip + 4, n, lane);
+            emit_copy_v1(o, ip - c, m, lane);
+            ip += m;
+            next_emit = ip;
+            if (ip >= ip_limit) break;  // :381-384
+            if (lane == 0) {            // :393-394
+                const uint32_t x1 = ld_le32(in + ip - 1);
+                __stcg(table + (table_hash<HASH_MODE>(x1, mask, lut) >> 1), (ip - 1) | (fp16(x1) << 16));
+            }
+            __syncwarp();
+            reprobe = true;
+            kb = 0;
+        }
+    }
+    if (next_emit < n) emit_literal_v1(o, in + next_emit, n - next_emit, lane);  // :406-411
+}
+
 template <int HASH_MODE>
 __global__ void __launch_bounds__(256)
 k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
               const uint32_t *__restrict__ in_len, uint8_t *out_base,
               const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
               uint32_t *__restrict__ out_len, int32_t *__restrict__ status, size_t n_items, int frag_mode,
-              unsigned long long *__restrict__ next_item, uint16_t *__restrict__ tables) {
+              unsigned long long *__restrict__ next_item, uint32_t *__restrict__ tables) {
     __shared__ uint16_t lut[1024];
     __shared__ uint32_t sched[SNP_SCHED_LEN];
     if (HASH_MODE == SNP_HASH_CRC32C) build_crc_lut(lut, threadIdx.x, blockDim.x);
@@ -231,7 +324,7 @@ k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
     const unsigned warps = blockDim.x / SNP_WARP;
     const unsigned warp = threadIdx.x / SNP_WARP;
     const unsigned lane = lane_id();
-    uint16_t *table = tables + ((size_t)blockIdx.x * warps + warp) * 16384;
+    uint32_t *table = tables + ((size_t)blockIdx.x * warps + warp) * 16384;
 
     for (;;) {
         unsigned long long item = 0;
@@ -251,7 +344,7 @@ k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
                 if ((int)lane < need) o.put(lane, (uint8_t)(lane < 4 ? lo >> (8 * lane) : hi));
                 o.pos = need;
             }
-            if (n > 0) compress_fragment_v2<HASH_MODE, true>(in, n, o, table, lut, sched);
+            if (n > 0) compress_fragment_v3<HASH_MODE>(in, n, o, table, lut, sched);
             if (o.pos > o.cap) st = SNP_OUTPUT_TOO_SMALL;  // SnappyCompressor.cs:63-68
         }
         if (lane == 0) {

@@ -213,15 +213,15 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
         const int cps = c->comp_ctas_per_sm;
         size_t ctas3 = (n + wpc - 1) / wpc;
         unsigned grid3 = (unsigned)std::min(ctas3, (size_t)c->sm_count * cps);
-        if ((rc = c->d_tables.reserve((size_t)c->sm_count * cps * wpc * 32768))) return rc;
+        if ((rc = c->d_tables.reserve((size_t)c->sm_count * cps * wpc * 65536))) return rc;
         if (hash_mode == SNP_HASH_CRC32C)
             snp::k_compress_v3<SNP_HASH_CRC32C><<<grid3, wpc * SNP_WARP, 0, s>>>(
                 in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr,
-                (uint16_t *)c->d_tables.p);
+                (uint32_t *)c->d_tables.p);
         else
             snp::k_compress_v3<SNP_HASH_MUL><<<grid3, wpc * SNP_WARP, 0, s>>>(
                 in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr,
-                (uint16_t *)c->d_tables.p);
+                (uint32_t *)c->d_tables.p);
     } else {
         unsigned long long *ctr;
         if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
