@@ -79,17 +79,19 @@ def make_blocks(torch, corpus_dev, first_block: int, count: int, dev, force_clas
         rows = pick(lo, hi)
         if rows.numel():
             windows(name, rows)
-    rows = pick(67, 80)  # LZ-synthetic: 32 fresh bytes + a 32-byte match 1..32 KiB back, built sequentially
-    if rows.numel():  # so that every match is a true copy of what precedes it (sources start inside a fresh run,
-        n = rows.numel()  # where the reference's probe loop has inserted every position)
+    rows = pick(67, 80)  # LZ-synthetic: 64-byte segments = 32 fresh bytes + a 32-byte match that is a true copy of
+    if rows.numel():  # the fresh run of a segment 1..32 KiB back (where the reference's probe loop has inserted
+        n = rows.numel()  # every position, so its compressor finds the match: ratio ~0.59)
         R = torch.randint(0, 256, (n, BLOCK), device=dev, generator=g, dtype=torch.int32).to(torch.uint8)
         nseg = BLOCK // 64
-        back = torch.randint(16, 512, (n, nseg), device=dev, generator=g)       # segments back: 1..32 KiB
-        inner = torch.randint(0, 29, (n, nseg), device=dev, generator=g)        # start inside the fresh run
+        seg = torch.arange(nseg, device=dev)
+        back = torch.randint(16, 512, (n, nseg), device=dev, generator=g)  # segments back: 1..32 KiB
+        src_seg = torch.where(seg >= 16, seg - torch.minimum(back, seg.unsqueeze(0).expand(n, -1)), seg)
         k32 = torch.arange(32, device=dev)
-        for sgm in range(16, nseg):
-            src0 = (sgm - torch.minimum(back[:, sgm], torch.full_like(back[:, sgm], sgm))) * 64 + inner[:, sgm]
-            R[:, sgm * 64 + 32: sgm * 64 + 64] = R.gather(1, src0.unsqueeze(1) + k32)
+        src = (src_seg.unsqueeze(2) * 64 + k32).view(n, nseg * 32)          # fresh run of the source segment
+        v = R.view(n, nseg, 64)
+        copy = R.gather(1, src).view(n, nseg, 32)
+        v[:, 16:, 32:] = copy[:, 16:, :]
         out[rows] = R
     rows = pick(80, 90)  # database-like fixed-width records
     if rows.numel():
@@ -323,6 +325,11 @@ def run_compress(args, torch, dist, engine, world, rank, local, dev):
     pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pp):
         peak = float(json.load(open(pp))["hbm_gbs"])
+    ctraffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        pb = json.load(open(tp)).get("compress_dram_bytes_per_block")
+        ctraffic = int(pb * n) if pb else None
     if rank == 0:
         print(json.dumps({
             "metric": "uncompressed GB/s (batched compress, 64 KiB blocks)", "value": round(n * BLOCK / ms / 1e6, 2),
@@ -331,7 +338,7 @@ def run_compress(args, torch, dist, engine, world, rank, local, dev):
             "config": {"workload": f"batched compress: {n} x 64 KiB raw blocks per GPU (50 % compressible synthetic), device-resident",
                        "ratio": round(cbytes / (n * BLOCK), 4), "hash_mode": "crc32c"},
             "roofline": {"bound": "hbm", "achieved": round((n * BLOCK + cbytes) / ms / 1e6, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round((n * BLOCK + cbytes) / ms / 1e6 / peak, 4), "traffic": None, "kernel": "snp::k_compress"},
+                         "frac": round((n * BLOCK + cbytes) / ms / 1e6 / peak, 4), "traffic": ctraffic, "kernel": "snp::k_compress_v3"},
             "gpu_launches": args.steps, "clocks": clk.summary()}))
 
 
