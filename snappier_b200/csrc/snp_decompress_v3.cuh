@@ -45,6 +45,9 @@ __device__ __forceinline__ uint32_t tag_lut3_entry(uint32_t c) {
     return len | (hdr << 8) | ((32 - 8 * (hdr - 1)) << 16) | flags;
 }
 
+#ifndef SNP_V3_CTAS
+#define SNP_V3_CTAS 8
+#endif
 #define SNP_QCAP 64  // queue entries per warp (power of two)
 
 struct WarpQueue3 {
@@ -244,7 +247,7 @@ __device__ __noinline__ int decompress_block_v3(const uint8_t *__restrict__ in, 
 // Persistent launch: one CTA slot per (SM x resident CTA); every warp pulls the next block
 // index from a global counter, so cheap (incompressible) and expensive (text) blocks balance
 // across warps instead of leaving warp slots idle until the slowest warp of a CTA retires.
-__global__ void __launch_bounds__(256, 8)
+__global__ void __launch_bounds__(256, SNP_V3_CTAS)
 k_decompress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
                 const uint32_t *__restrict__ in_len, uint8_t *out_base,
                 const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,

@@ -176,7 +176,7 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
         unsigned long long *ctr;
         int rc = ctx_work_counter(c, s, &ctr);
         if (rc) return rc;
-        unsigned pgrid = (unsigned)(c->sm_count * (c->decomp_kernel == 3 ? 8 : 6));
+        unsigned pgrid = (unsigned)(c->sm_count * (c->decomp_kernel == 3 ? SNP_V3_CTAS : 6));
         if (pgrid > grid) pgrid = grid;
         if (c->decomp_kernel == 3)
             snp::k_decompress_v3<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
