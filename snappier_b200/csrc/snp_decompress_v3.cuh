@@ -15,6 +15,7 @@
 // 556-611 (one-shot); identical results to v1, v2 and oracle/snappy_oracle.c.
 #pragma once
 #include "snp_common.cuh"
+#include "snp_decompress_v1.cuh"
 
 namespace snp {
 
@@ -265,7 +266,11 @@ k_decompress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict_
         item = __shfl_sync(SNP_FULL, item, 0);
         if (item >= n_items) break;
         uint32_t w = 0;
-        int st = decompress_block_v3(in_base + in_off[item], in_len[item], out_base + out_off[item],
+        int st;
+        if (in_len[item] >= 0x7fff0000u)  // stream offsets are 32-bit with headroom here; v1 is safe to 2^32-1
+            st = decompress_block_v1(in_base + in_off[item], in_len[item], out_base + out_off[item], out_cap[item], &w);
+        else
+            st = decompress_block_v3(in_base + in_off[item], in_len[item], out_base + out_off[item],
                                      out_cap[item], &w, lut, q);
         if (lane == 0) {
             out_len[item] = w;

@@ -350,7 +350,11 @@ k_decompress_v4(const uint8_t *__restrict__ in_base, const uint64_t *__restrict_
         item = __shfl_sync(SNP_FULL, item, 0);
         if (item >= n_items) break;
         uint32_t w = 0;
-        int st = decompress_block_v4(in_base + in_off[item], in_len[item], out_base + out_off[item],
+        int st;
+        if (in_len[item] >= 0x7fff0000u)
+            st = decompress_block_v1(in_base + in_off[item], in_len[item], out_base + out_off[item], out_cap[item], &w);
+        else
+            st = decompress_block_v4(in_base + in_off[item], in_len[item], out_base + out_off[item],
                                      out_cap[item], &w, lut, q, ring, phases);
         if (lane == 0) {
             out_len[item] = w;

@@ -175,6 +175,44 @@ def test_bad_data_statuses(engine, oracle, fixtures):
     assert S.decompress_to_array(b"\x00") == b""
 
 
+def test_copy4_long_literals_and_big_blocks(engine, oracle):
+    """Tag forms the reference compressor never emits but its decoder accepts (SnappyDecompressor.cs:305-313:
+    COPY4; :278-288: 2/3/4-byte literal lengths), plus blocks far above 64 KiB decoded by one warp."""
+    from snappier_b200.batch import decompress_many
+    rng = np.random.default_rng(12)
+    lit = rng.integers(0, 256, size=70000, dtype=np.uint8).tobytes()
+
+    def varint(v):
+        out = bytearray()
+        while v >= 0x80:
+            out.append((v & 0x7f) | 0x80)
+            v >>= 7
+        out.append(v)
+        return bytes(out)
+
+    items = []
+    # literal with a 3-byte length, then COPY4 reaching 69000 bytes back, then an overlapping COPY4 (pattern fill)
+    body = bytes([62 << 2]) + (len(lit) - 1).to_bytes(3, "little") + lit
+    body += bytes([((10 - 1) << 2) | 3]) + (69000).to_bytes(4, "little")
+    body += bytes([((64 - 1) << 2) | 3]) + (3).to_bytes(4, "little")
+    items.append(varint(70000 + 10 + 64) + body)
+    # literal with a 4-byte length field; literal with a 2-byte length field
+    items.append(varint(70000) + bytes([63 << 2]) + (len(lit) - 1).to_bytes(4, "little") + lit)
+    items.append(varint(300) + bytes([61 << 2]) + (299).to_bytes(2, "little") + lit[:300])
+    # COPY4 with offset 0 / beyond the produced data -> invalid copy offset
+    items.append(varint(20) + bytes([3 << 2]) + b"abcd" + bytes([(4 - 1) << 2 | 3]) + (0).to_bytes(4, "little"))
+    items.append(varint(20) + bytes([3 << 2]) + b"abcd" + bytes([(4 - 1) << 2 | 3]) + (5).to_bytes(4, "little"))
+    # multi-megabyte blocks: repetitive (long copies) and text-like
+    items.append(oracle.compress(b"0123456789abcdef" * 200000)[1])
+    items.append(oracle.compress(b"".join(H.synthetic_blocks(3, 40)))[1])
+    caps = [oracle.uncompressed_length(b)[1] for b in items]
+    got, status = decompress_many(engine, items, caps)
+    for i, b in enumerate(items):
+        st, dec = oracle.decompress(b, cap=caps[i])
+        assert status[i] == st and got[i] == dec, i
+    assert status[0] == 0 and status[3] == oracle.INVALID_COPY_OFFSET and status[4] == oracle.INVALID_COPY_OFFSET
+
+
 def test_hypothesis_fuzz_decoder_never_diverges(engine, oracle):
     """Random byte soup and mutated valid blocks: status and output always equal the oracle's."""
     from snappier_b200.batch import decompress_many
