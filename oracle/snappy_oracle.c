@@ -308,11 +308,24 @@ int orc_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t
                                  : (kind == 1 ? 1 : kind == 2 ? 2 : 4);
         if ((size_t)(end - ip) < 1 + extra) break; /* RefillTag -> truncated tag, :464-483 */
         uint64_t trailer = 0;
-        for (size_t i = 0; i < extra; i++) trailer |= (uint64_t)ip[1 + i] << (8 * i);
+        if ((size_t)(end - ip) >= 5) { /* one unaligned load instead of a byte loop (the reference's preload) */
+            uint32_t t32;
+            memcpy(&t32, ip + 1, 4);
+            trailer = extra == 4 ? t32 : (t32 & ((1u << (8 * extra)) - 1u));
+        } else {
+            for (size_t i = 0; i < extra; i++) trailer |= (uint64_t)ip[1 + i] << (8 * i);
+        }
         ip += 1 + extra;
         if (kind == 0) {
             uint64_t len = ((c >> 2) >= 60 ? trailer : (uint64_t)(c >> 2)) + 1; /* :264-288 */
             uint64_t avail = (uint64_t)(end - ip);
+            /* TryFastAppend (:579-589): short literal, 16 bytes of slack on both sides */
+            if (len <= 16 && avail >= 16 + 5 && U - op >= 16) {
+                memcpy(out + op, ip, 16);
+                op += (size_t)len;
+                ip += len;
+                continue;
+            }
             uint64_t take = len < avail ? len : avail; /* :290-297 partial literal */
             if (take > U - op) return ORC_DATA_TOO_LONG;  /* :570-573 */
             memcpy(out + op, ip, (size_t)take);
@@ -330,11 +343,17 @@ int orc_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t
             }
             if (offset == 0 || op < offset) return ORC_INVALID_COPY_OFFSET; /* :598-601 */
             if (len > U - op) return ORC_DATA_TOO_LONG;                      /* :603-606 */
-            /* CopyHelpers.cs:222-230: forward byte order (pattern replication) */
-            if (offset >= len)
-                memcpy(out + op, out + op - offset, (size_t)len);
-            else
-                for (uint64_t k = 0; k < len; k++) out[op + k] = out[op - offset + k];
+            /* CopyHelpers.cs:64-230: forward byte order (pattern replication); the wide paths are
+             * speed devices with identical results */
+            uint8_t *d = out + op;
+            const uint8_t *s = d - offset;
+            if (offset >= 8 && U - op >= len + 8) { /* 8 bytes at a time never reads unwritten bytes */
+                for (uint64_t k = 0; k < len; k += 8) memcpy(d + k, s + k, 8);
+            } else if (offset >= len) {
+                memcpy(d, s, (size_t)len);
+            } else {
+                for (uint64_t k = 0; k < len; k++) d[k] = s[k];
+            }
             op += (size_t)len;
         }
     }
