@@ -309,7 +309,144 @@ __device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in
     if (next_emit < n) emit_literal_v1(o, in + next_emit, n - next_emit, lane);  // :406-411
 }
 
+// ---- compress_fragment_v4: v3 with the dependent memory round trips per match cut from ~5 to ~2 ----
+//  * the 32 probe words of a run's first batch (and the re-probe / ip-1 words) come from a 128-byte
+//    register window of the input (one coalesced load per ~90 bytes of progress, SHFL + funnel shift
+//    per probe) instead of two global loads per lane per batch;
+//  * the ip-1 table insert (SnappyCompressor.cs:393-394) is deferred to the top of the next batch,
+//    where its word comes from the same window -- still before any table read of that batch;
+//  * a candidate that survives the fingerprint filter is verified with a 16-byte read, so the hit
+//    lane already knows whether the match is shorter than 12 bytes (most are) and FindMatchLength's
+//    own round trip is only paid for longer matches.
 template <int HASH_MODE>
+__device__ __noinline__ void compress_fragment_v4(const uint8_t *__restrict__ in, uint32_t n, OutCursor &o,
+                                                  uint32_t *table, const uint16_t *lut, const uint32_t *sched) {
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const int tsize = table_size_for(n);
+    const uint32_t mask = 2u * (uint32_t)(tsize - 1);
+    uint32_t next_emit = 0;
+    if (n >= 15) {  // Constants.InputMarginBytes, SnappyCompressor.cs:190
+        {  // HashTable.cs:52: "zero" = position 0, whose bytes are in[0..3]
+            const uint32_t e0 = fp16(ld_le32(in)) << 16;
+            uint4 z = make_uint4(e0, e0, e0, e0);
+            uint4 *t4 = reinterpret_cast<uint4 *>(table);
+            for (int i = lane; i < tsize / 4; i += SNP_WARP) __stcg(t4 + i, z);
+            __syncwarp();
+        }
+        const uint32_t ip_limit = n - 15;
+        const uint32_t skew = (uint32_t)((uintptr_t)in & 3);
+        const uint32_t *in_w = (const uint32_t *)((uintptr_t)in - skew);
+        const uint32_t last_w = (skew + n - 1) >> 2;
+        uint32_t wword = 0x7fffffffu, W = 0;  // window: lane holds in_w[wword + lane]
+        auto win_le32 = [&](uint32_t pos) -> uint32_t {
+            const uint32_t bo = skew + pos;
+            const uint32_t idx = (bo >> 2) - wword;
+            const uint32_t lo = __shfl_sync(SNP_FULL, W, idx);
+            const uint32_t hi = __shfl_sync(SNP_FULL, W, idx + 1);
+            return __funnelshift_r(lo, hi, (bo & 3) * 8);
+        };
+        bool reprobe = false;
+        uint32_t kb = 0;
+        for (;;) {
+            uint32_t p, nip;
+            bool term = false;
+            if (reprobe && lane == 0) {
+                p = next_emit;
+                nip = p;
+            } else {
+                const uint32_t k = kb + lane - (reprobe ? 1u : 0u);
+                const uint32_t s = sched[min(k, (uint32_t)SNP_SCHED_LEN - 1)];
+                p = next_emit + 1 + (s & 0xfffffu);
+                nip = p + (s >> 20);
+                term = nip > ip_limit || k >= SNP_SCHED_LEN;  // :323-327
+            }
+            const unsigned terms = __ballot_sync(SNP_FULL, term);
+            const unsigned live = terms ? ((1u << (__ffs(terms) - 1)) - 1u) : SNP_FULL;
+            const bool is_live = (live >> lane) & 1;
+            const bool first = kb == 0;  // probes at next_emit .. next_emit+32: served by the window
+            uint32_t x;
+            if (first) {
+                const uint32_t lo_pos = next_emit - (reprobe ? 1u : 0u);
+                const uint32_t wlo = (skew + lo_pos) >> 2;
+                const uint32_t whi = (skew + min(next_emit + 48u, n) + 3) >> 2;  // probes + 12 bytes of extension
+                if (wlo < wword || whi + 1 > wword + SNP_WARP) {
+                    wword = wlo;
+                    W = in_w[min(wword + lane, last_w)];
+                }
+                x = win_le32(is_live ? p : lo_pos);
+                if (reprobe) {  // deferred :393-394, before any table read of this batch
+                    const uint32_t x1 = win_le32(next_emit - 1);
+                    if (lane == 0)
+                        __stcg(table + (table_hash<HASH_MODE>(x1, mask, lut) >> 1), (next_emit - 1) | (fp16(x1) << 16));
+                    __syncwarp();
+                }
+            } else {
+                x = is_live ? ld_le32(in + p) : 0u;
+            }
+            const uint32_t h = is_live ? (table_hash<HASH_MODE>(x, mask, lut) >> 1) : (0x10000u + lane);
+            const unsigned same = __match_any_sync(SNP_FULL, h);
+            const unsigned lower = same & lt;
+            const int src = lower ? 31 - __clz(lower) : (int)lane;
+            const uint32_t p_src = __shfl_sync(SNP_FULL, p, src);
+            const uint32_t x_src = __shfl_sync(SNP_FULL, x, src);
+            uint32_t cand = 0, ext1 = 0, ext2 = 0;
+            bool hit = false, has_ext = false;
+            if (is_live) {
+                if (lower) {  // an earlier probe of this batch owns the bucket: its bytes are in a register
+                    cand = p_src;
+                    hit = x_src == x;
+                } else {
+                    const uint32_t e = __ldcg(table + h);
+                    cand = e & 0xffffu;
+                    if ((e >> 16) == fp16(x)) {  // cand + 16 <= n: cand < p <= ip_limit - 1 = n - 16
+                        const uint32_t a = skew + cand;
+                        const uint32_t *wp = in_w + (a >> 2);
+                        const unsigned sh = (a & 3) * 8;
+                        const uint32_t q0 = wp[0], q1 = wp[1], q2 = wp[2], q3 = wp[3];
+                        hit = __funnelshift_r(q0, q1, sh) == x;
+                        ext1 = __funnelshift_r(q1, q2, sh);  // bytes cand+4 .. cand+7
+                        ext2 = __funnelshift_r(q2, q3, sh);  // bytes cand+8 .. cand+11
+                        has_ext = true;
+                    }
+                }
+            }
+            const unsigned hits = __ballot_sync(SNP_FULL, hit);
+            const int f = __ffs(hits) - 1;
+            const unsigned commit = hits ? (live & (0xffffffffu >> (31 - f))) : live;
+            if (((commit >> lane) & 1) && (same & commit & ~lt & ~(1u << lane)) == 0)
+                __stcg(table + h, p | (fp16(x) << 16));
+            __syncwarp();
+            if (!hits) {
+                if (terms) break;
+                kb += reprobe ? 31u : 32u;
+                reprobe = false;
+                continue;
+            }
+            uint32_t ip = __shfl_sync(SNP_FULL, p, f);
+            const uint32_t c = __shfl_sync(SNP_FULL, cand, f);
+            if (ip > next_emit) emit_literal_v1(o, in + next_emit, ip - next_emit, lane);
+            uint32_t m;
+            if (first && __shfl_sync(SNP_FULL, (int)has_ext, f)) {  // ip + 12 <= n always (ip < ip_limit)
+                const uint32_t d1 = __shfl_sync(SNP_FULL, ext1, f) ^ win_le32(ip + 4);
+                const uint32_t d2 = __shfl_sync(SNP_FULL, ext2, f) ^ win_le32(ip + 8);
+                const uint32_t matched = d1 ? (uint32_t)(__ffs(d1) - 1) >> 3 : (d2 ? 4u + ((uint32_t)(__ffs(d2) - 1) >> 3) : 8u);
+                m = matched < 8 ? 4 + matched : 12 + find_match_length_v2(in, c + 12, ip + 12, n, lane);
+            } else {
+                m = 4 + find_match_length_v2(in, c + 4, ip + 4, n, lane);
+            }
+            emit_copy_v1(o, ip - c, m, lane);
+            ip += m;
+            next_emit = ip;
+            if (ip >= ip_limit) break;  // :381-384
+            reprobe = true;             // :393-398 happen at the top of the next batch
+            kb = 0;
+        }
+    }
+    if (next_emit < n) emit_literal_v1(o, in + next_emit, n - next_emit, lane);  // :406-411
+}
+
+template <int HASH_MODE, int VARIANT = 3>
 __global__ void __launch_bounds__(256)
 k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
               const uint32_t *__restrict__ in_len, uint8_t *out_base,
@@ -344,7 +481,10 @@ k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
                 if ((int)lane < need) o.put(lane, (uint8_t)(lane < 4 ? lo >> (8 * lane) : hi));
                 o.pos = need;
             }
-            if (n > 0) compress_fragment_v3<HASH_MODE>(in, n, o, table, lut, sched);
+            if (n > 0) {
+                if (VARIANT == 4) compress_fragment_v4<HASH_MODE>(in, n, o, table, lut, sched);
+                else compress_fragment_v3<HASH_MODE>(in, n, o, table, lut, sched);
+            }
             if (o.pos > o.cap) st = SNP_OUTPUT_TOO_SMALL;  // SnappyCompressor.cs:63-68
         }
         if (lane == 0) {

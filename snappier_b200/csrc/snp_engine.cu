@@ -98,7 +98,8 @@ struct snp_ctx {
     int sm_count = 148;
     int decomp_kernel = 3;  // SNP_DECOMP_KERNEL (1 = baseline, 2/3 = warp-parallel, 4 = 3 + TMA-staged input;
                             // measured 10 % slower than 3 because the kernel is issue-bound)
-    int comp_kernel = 2;    // SNP_COMP_KERNEL (1 = baseline, 2 = warp-parallel probes)
+    int comp_kernel = 3;    // SNP_COMP_KERNEL (1 = baseline, 2 = smem tables, 3 = L2 tables, 4 = 3 + register window;
+                            // 4 measured equal to 3: the kernel is bound by random table sectors)
     DevBuf d_in, d_out, d_meta, d_tmp;
     DevBuf d_tables;           // k_compress_v3: one 32 KiB hash table per resident warp
     int comp_ctas_per_sm = 8;  // SNP_COMP_CTAS_PER_SM (x 8 warps)
@@ -214,14 +215,18 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
         size_t ctas3 = (n + wpc - 1) / wpc;
         unsigned grid3 = (unsigned)std::min(ctas3, (size_t)c->sm_count * cps);
         if ((rc = c->d_tables.reserve((size_t)c->sm_count * cps * wpc * 65536))) return rc;
-        if (hash_mode == SNP_HASH_CRC32C)
-            snp::k_compress_v3<SNP_HASH_CRC32C><<<grid3, wpc * SNP_WARP, 0, s>>>(
-                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr,
-                (uint32_t *)c->d_tables.p);
-        else
-            snp::k_compress_v3<SNP_HASH_MUL><<<grid3, wpc * SNP_WARP, 0, s>>>(
-                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr,
-                (uint32_t *)c->d_tables.p);
+#define SNP_LAUNCH_C3(H, V)                                                                                  \
+    snp::k_compress_v3<H, V><<<grid3, wpc * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap, \
+                                                              out_len, status, n, frag_mode, ctr,                  \
+                                                              (uint32_t *)c->d_tables.p)
+        if (c->comp_kernel == 3) {
+            if (hash_mode == SNP_HASH_CRC32C) SNP_LAUNCH_C3(SNP_HASH_CRC32C, 3);
+            else SNP_LAUNCH_C3(SNP_HASH_MUL, 3);
+        } else {
+            if (hash_mode == SNP_HASH_CRC32C) SNP_LAUNCH_C3(SNP_HASH_CRC32C, 4);
+            else SNP_LAUNCH_C3(SNP_HASH_MUL, 4);
+        }
+#undef SNP_LAUNCH_C3
     } else {
         unsigned long long *ctr;
         if ((rc = ctx_work_counter(c, s, &ctr))) return rc;

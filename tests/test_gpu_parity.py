@@ -306,6 +306,12 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     c1, s1 = compress_many(e1, blocks, 0)
     c2, s2 = compress_many(e2, blocks, 0)
     assert c1 == c2 and not s1.any() and not s2.any()
+    for variant in ("2", "4"):  # shared-memory tables; L2 tables + register window
+        ev = _engine_with({"SNP_COMP_KERNEL": variant})
+        for mode in (0, 1):
+            cv, sv = compress_many(ev, blocks, mode)
+            assert not sv.any() and cv == (c1 if mode == 0 else [oracle.compress(b, 1)[1] for b in blocks]), variant
+        ev.close()
     rng = np.random.default_rng(17)
     items = list(c1)
     for c in c1[:40]:
