@@ -333,3 +333,50 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     e1.close()
     e2.close()
     e4.close()
+
+
+def test_single_call_api_is_thread_safe(oracle):
+    """Snappy.* are static and re-entrant (SURVEY 8(b) "Threading"): concurrent calls from several
+    threads, each on its lazily created thread-local context, all give oracle bytes."""
+    import threading
+    from snappier_b200 import snappy as S
+    blocks = H.synthetic_blocks(4242, 24, size=20000)
+    want = [oracle.compress(b)[1] for b in blocks]
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(3):
+                for i in range(tid, len(blocks), 4):
+                    c = S.compress_to_array(blocks[i])
+                    assert c == want[i]
+                    assert S.decompress_to_array(c) == blocks[i]
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
+
+
+def test_argument_errors(engine):
+    """Call-level failures are negative codes, never crashes."""
+    import ctypes as C
+    from snappier_b200 import _native as N
+    L = N.lib()
+    w = C.c_size_t(0)
+    buf = np.zeros(64, np.uint8)
+    assert L.snp_compress(buf.ctypes.data, 8, buf.ctypes.data, 64, C.byref(w), 7) == N.E_INVALID_ARG  # bad hash mode
+    assert L.snp_compress(buf.ctypes.data, 8, buf.ctypes.data + 4, 60, C.byref(w), 0) == N.E_OVERLAP
+    assert L.snp_compress(None, 8, buf.ctypes.data, 64, C.byref(w), 0) == N.E_INVALID_ARG
+    assert L.snp_decompress_batch(None, buf.ctypes.data, None, None, None, None, None, None, None, 3, 0, None) == N.E_INVALID_ARG
+    assert L.snp_decompress_batch(None, None, None, None, None, None, None, None, None, 0, 0, None) == N.OK  # empty batch
+    # an oversized item in a compress batch is reported per item, neighbours unaffected
+    from snappier_b200.batch import pack
+    items = [b"a" * 100, b"b" * 70000, b"c" * 100]
+    base, off, ln = pack(items)
+    out = np.zeros(3 * 80000, np.uint8)
+    out_len, status = engine.compress_batch_host(base, off, ln, out, np.arange(3, dtype=np.uint64) * 80000,
+                                                 np.full(3, 80000, np.uint32))
+    assert status[0] == 0 and status[2] == 0 and status[1] == N.E_INVALID_ARG and out_len[1] == 0
