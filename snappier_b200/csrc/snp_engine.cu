@@ -22,6 +22,7 @@
 #include "snp_decompress_v2.cuh"
 #include "snp_decompress_v3.cuh"
 #include "snp_decompress_v4.cuh"
+#include "snp_decompress_v5.cuh"
 #include "snp_frame.cuh"
 
 namespace {
@@ -96,7 +97,8 @@ struct snp_ctx {
     std::mutex mu;
     std::atomic<uint64_t> launches{0};
     int sm_count = 148;
-    int decomp_kernel = 3;  // SNP_DECOMP_KERNEL (1 = baseline, 2/3 = warp-parallel, 4 = 3 + TMA-staged input;
+    int decomp_kernel = 5;  // SNP_DECOMP_KERNEL (1 = baseline, 2/3 = warp-parallel, 5 = 3 + sparse-tag prefix engine,
+                            // 4 = 3 + TMA-staged input;
                             // measured 10 % slower than 3 because the kernel is issue-bound)
     int comp_kernel = 3;    // SNP_COMP_KERNEL (1 = baseline, 2 = smem tables, 3 = L2 tables, 4 = 3 + register window;
                             // 4 measured equal to 3: the kernel is bound by random table sectors)
@@ -177,10 +179,13 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
         unsigned long long *ctr;
         int rc = ctx_work_counter(c, s, &ctr);
         if (rc) return rc;
-        unsigned pgrid = (unsigned)(c->sm_count * (c->decomp_kernel == 3 ? SNP_V3_CTAS : 6));
+        unsigned pgrid = (unsigned)(c->sm_count * (c->decomp_kernel == 4 ? 6 : SNP_V3_CTAS));
         if (pgrid > grid) pgrid = grid;
         if (c->decomp_kernel == 3)
             snp::k_decompress_v3<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
+                                                                    out_cap, out_len, status, n, ctr);
+        else if (c->decomp_kernel == 5)
+            snp::k_decompress_v5<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
                                                                     out_cap, out_len, status, n, ctr);
         else
             snp::k_decompress_v4<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
@@ -569,7 +574,7 @@ int snp_create(int device, snp_ctx **out) {
     snp::k_init_probe_sched<<<1, 32, 0, c->stream>>>();
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 3);
+    c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 5);
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     *out = c.release();

@@ -301,6 +301,8 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     e1 = _engine_with({"SNP_DECOMP_KERNEL": "1", "SNP_COMP_KERNEL": "1"})
     e2 = _engine_with({})
     e4 = _engine_with({"SNP_DECOMP_KERNEL": "4"})  # TMA-staged input ring
+    e5 = _engine_with({"SNP_DECOMP_KERNEL": "5"})  # sparse-tag prefix engine + dense engine
+    e3 = _engine_with({"SNP_DECOMP_KERNEL": "3"})
     _, blocks = _corpus_blocks(fixtures)
     blocks = blocks + H.synthetic_blocks(5150, 48)
     c1, s1 = compress_many(e1, blocks, 0)
@@ -325,14 +327,29 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     assert d2[:len(blocks)] == blocks
     d4, s4 = decompress_many(e4, items, caps)
     assert np.array_equal(s4, s2) and d4 == d2
+    for ex in (e3, e5):
+        dx, sx = decompress_many(ex, items, caps)
+        assert np.array_equal(sx, s1) and dx == d1
     # ragged / tiny / unaligned inputs through the ring's head-tail byte path
     small = [oracle.compress(b[:n])[1] for b in blocks[:8] for n in (0, 1, 5, 15, 16, 17, 31, 33, 255, 257, 511, 513, 1023, 1500)]
     d4s, s4s = decompress_many(e4, small)
     d2s, s2s = decompress_many(e2, small)
     assert d4s == d2s and not s4s.any()
+    # long literals at every source/destination alignment (the vectorised literal path of kernel 5)
+    rng2 = np.random.default_rng(23)
+    lits = []
+    for n in (127, 128, 129, 143, 144, 145, 300, 1000, 4097, 70001):
+        for pad in (0, 1, 5, 15):
+            raw = rng2.integers(0, 256, size=n + pad, dtype=np.uint8).tobytes()
+            lits.append(oracle.compress(raw)[1])  # incompressible -> (pad-shifted) long literals
+    for ex in (e1, e3, e5):
+        dl, sl = decompress_many(ex, lits)
+        assert not sl.any() and dl == [oracle.decompress(c)[1] for c in lits]
     e1.close()
     e2.close()
+    e3.close()
     e4.close()
+    e5.close()
 
 
 def test_single_call_api_is_thread_safe(oracle):
