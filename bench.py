@@ -237,6 +237,34 @@ def cpu_reference_run(comp_host: np.ndarray, off: np.ndarray, ln: np.ndarray, th
     return passes * n * BLOCK / dt / 1e9, passes, dt
 
 
+def sanity_anchor(comp_host: np.ndarray, off: np.ndarray, ln: np.ndarray, max_blocks: int = 1024):
+    """Google's C++ Snappy (pyarrow's bundled codec), one thread, same blocks: an independent yard-stick for
+    the oracle port.  None when pyarrow lacks the codec."""
+    try:
+        import pyarrow as pa
+        codec = pa.Codec("snappy")
+    except Exception:
+        return None
+    n = min(len(off), max_blocks)
+    blocks = [comp_host[int(off[i]): int(off[i]) + int(ln[i])].tobytes() for i in range(n)]
+    t0 = time.perf_counter()
+    for b in blocks:
+        codec.decompress(b, decompressed_size=BLOCK)
+    return round(n * BLOCK / (time.perf_counter() - t0) / 1e9, 3)
+
+
+def dotnet_probe():
+    """the real C# reference can only be timed where a .NET SDK exists."""
+    import shutil
+    exe = shutil.which("dotnet")
+    if not exe:
+        return None
+    try:
+        return subprocess.run([exe, "--version"], capture_output=True, text=True, timeout=20).stdout.strip() or None
+    except Exception:
+        return None
+
+
 def host_sample_blocks(n_blocks: int, first_block: int = 0):
     """CPU-only construction of a bounded sample of the workload for --impl reference (no GPU)."""
     import torch
@@ -481,9 +509,15 @@ def main():
         threads = os.cpu_count() or 1
         v, passes, dt = cpu_reference_run(comp[:cb].cpu().numpy(), c_off[:nc].cpu().numpy().astype(np.uint64),
                                           c_len[:nc].cpu().numpy().astype(np.uint32), threads, args.cpu_seconds)
+        h_comp = comp[:cb].cpu().numpy()
+        h_off = c_off[:nc].cpu().numpy().astype(np.uint64)
+        h_len = c_len[:nc].cpu().numpy().astype(np.uint32)
+        dn = dotnet_probe()
         cpu = {"value": round(v, 3), "unit": "GB/s", "cores": threads, "kind": "port",
                "sample": f"first {nc} blocks of rank 0's batch, {passes} passes in {dt:.1f} s, oracle C port of the "
-                         f"reference algorithm (Snappier's C# cannot run here: no .NET)"}
+                         f"reference algorithm (Snappier's C# cannot run here: " +
+                         (f"dotnet {dn} found, see csharp/Bench)" if dn else "no .NET SDK)"),
+               "google_snappy_1thread_GBps": sanity_anchor(h_comp, h_off, h_len), "dotnet": dn}
 
     print(json.dumps({
         "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
