@@ -330,8 +330,7 @@ struct Chunk {
 };
 
 int chunk_phase1(snp_ctx *c, const Chunk &ck, bool compress, const uint8_t *in_base, const uint64_t *in_off,
-                 const uint32_t *in_len, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
-                 int32_t *status, uint32_t hash_mode, std::vector<uint64_t> &rel) {
+                 const uint32_t *in_len, const uint64_t *out_off, const uint32_t *out_cap, uint32_t hash_mode) {
     snp_ctx::Slot &sl = c->slots[ck.slot];
     cudaStream_t s = sl.stream;
     const size_t n = ck.b - ck.a;
@@ -344,7 +343,6 @@ int chunk_phase1(snp_ctx *c, const Chunk &ck, bool compress, const uint8_t *in_b
     if ((rc = sl.h_meta.reserve(ml.bytes))) return rc;
     uint8_t *dm = (uint8_t *)sl.d_meta.p;
     uint8_t *hm = (uint8_t *)sl.h_meta.p;
-    (void)rel;
     {
         uint64_t *ri = (uint64_t *)(hm + ml.in_off), *ro = (uint64_t *)(hm + ml.out_off);
         for (size_t i = 0; i < n; i++) ri[i] = in_off[ck.a + i] - ck.si.lo;
@@ -369,9 +367,7 @@ int chunk_phase1(snp_ctx *c, const Chunk &ck, bool compress, const uint8_t *in_b
         rc = launch_decompress(c, s, (const uint8_t *)sl.d_in.p, d_in_off, d_in_len, (uint8_t *)sl.d_out.p,
                                d_out_off, d_out_cap, d_out_len, d_status, n);
     if (rc) return rc;
-    (void)out_len;
-    (void)status;
-    // out_len + status are contiguous: one D2H into the pinned mirror
+    // out_len + status are contiguous: one D2H into the pinned mirror (copied to the caller in phase 2)
     CU(cudaMemcpyAsync(hm + ml.out_len, dm + ml.out_len, ml.bytes - ml.out_len, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(sl.meta_ready, s));
     return SNP_OK;
@@ -412,7 +408,6 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
     }
     constexpr uint64_t kChunkBytes = 128ull << 20;  // per-chunk output span target
     constexpr size_t kChunkItems = 16384;
-    std::vector<uint64_t> rel;
     Chunk prev;
     bool have_prev = false;
     int rc = SNP_OK, k = 0;
@@ -432,7 +427,7 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
         }
         ck.b = b;
         ck.si.lo = ilo, ck.si.hi = ihi, ck.so.lo = olo, ck.so.hi = ohi;
-        rc = chunk_phase1(c, ck, compress, in_base, in_off, in_len, out_off, out_cap, out_len, status, hash_mode, rel);
+        rc = chunk_phase1(c, ck, compress, in_base, in_off, in_len, out_off, out_cap, hash_mode);
         if (rc == SNP_OK && have_prev) rc = chunk_phase2(c, prev, out_base, out_off, out_cap, out_len, status);
         prev = ck;
         have_prev = true;
