@@ -1,7 +1,9 @@
 // snp_common.cuh -- device-side helpers shared by the Snappy block kernels (sm_100a).
 #pragma once
 
+#ifndef SNP_EMU  // tests/cpp/simt_emu.h supplies the intrinsics for the host-side warp emulator
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/snappier_b200.h"
@@ -11,6 +13,10 @@
 
 namespace snp {
 
+#ifdef SNP_EMU
+__device__ __forceinline__ unsigned lane_id() { return (unsigned)simt::lane(); }
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << simt::lane()) - 1u; }
+#else
 __device__ __forceinline__ unsigned lane_id() {
     unsigned l;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
@@ -20,6 +26,35 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+}
+#endif
+
+// ---- tag table (replaces Constants.CharTable, Constants.cs:42-76) -----------
+// byte 0: length in the tag byte (literal n<60: n+1; copies: len)
+// byte 1: header bytes (tag byte + trailer): 1..5
+// byte 2: shift turning 0xffffffff into the trailer mask (32 - 8*trailer_bytes)
+// bits 24..26: COPY1 offset bits 8..10;  bit 30: literal length is in the trailer;  bit 31: literal
+__device__ __forceinline__ uint32_t tag_lut3_entry(uint32_t c) {
+    uint32_t kind = c & 3, n6 = c >> 2;
+    uint32_t len = 0, hdr, flags = 0;
+    if (kind == 0) {
+        flags = 0x80000000u;
+        if (n6 < 60) {
+            len = n6 + 1;
+            hdr = 1;
+        } else {
+            flags |= 0x40000000u;
+            hdr = 1 + (n6 - 59);
+        }
+    } else if (kind == 1) {
+        len = (n6 & 7) + 4;
+        hdr = 2;
+        flags = (c >> 5) << 24;
+    } else {
+        len = n6 + 1;
+        hdr = kind == 2 ? 3 : 5;
+    }
+    return len | (hdr << 8) | ((32 - 8 * (hdr - 1)) << 16) | flags;
 }
 
 // Unaligned little-endian 32-bit load from global or generic memory.  Touches only

@@ -19,32 +19,7 @@
 
 namespace snp {
 
-// byte 0: length in the tag byte (literal n<60: n+1; copies: len)
-// byte 1: header bytes (tag byte + trailer): 1..5
-// byte 2: shift turning 0xffffffff into the trailer mask (32 - 8*trailer_bytes)
-// bits 24..26: COPY1 offset bits 8..10;  bit 30: literal length is in the trailer;  bit 31: literal
-__device__ __forceinline__ uint32_t tag_lut3_entry(uint32_t c) {
-    uint32_t kind = c & 3, n6 = c >> 2;
-    uint32_t len = 0, hdr, flags = 0;
-    if (kind == 0) {
-        flags = 0x80000000u;
-        if (n6 < 60) {
-            len = n6 + 1;
-            hdr = 1;
-        } else {
-            flags |= 0x40000000u;
-            hdr = 1 + (n6 - 59);
-        }
-    } else if (kind == 1) {
-        len = (n6 & 7) + 4;
-        hdr = 2;
-        flags = (c >> 5) << 24;
-    } else {
-        len = n6 + 1;
-        hdr = kind == 2 ? 3 : 5;
-    }
-    return len | (hdr << 8) | ((32 - 8 * (hdr - 1)) << 16) | flags;
-}
+// tag_lut3_entry (the 256-entry tag table replacing Constants.CharTable) lives in snp_common.cuh
 
 #ifndef SNP_V3_CTAS
 #define SNP_V3_CTAS 8

@@ -267,7 +267,7 @@ def test_device_mode_large_batch_properties(engine, oracle):
     status2 = torch.full((n,), -99, dtype=torch.int32, device=dev)
     engine.decompress_batch_device(comp, c_off, c_len, out, o_off, o_cap, o_len, status2, stream)
     torch.cuda.synchronize()
-    assert engine.launch_count - before == 2
+    assert engine.launch_count - before == 3  # compress, then tag scan + decode (v6)
     assert int(status.abs().sum()) == 0 and int(status2.abs().sum()) == 0
     assert bool((o_len == 65536).all())
     want_len = np.array([len(oracle.compress(b)[1]) for b in blocks])
@@ -303,6 +303,7 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     e4 = _engine_with({"SNP_DECOMP_KERNEL": "4"})  # TMA-staged input ring
     e5 = _engine_with({"SNP_DECOMP_KERNEL": "5"})  # sparse-tag prefix engine + dense engine
     e3 = _engine_with({"SNP_DECOMP_KERNEL": "3"})
+    e6 = _engine_with({"SNP_DECOMP_KERNEL": "6", "SNP_V6_MIN_ITEMS": "1"})  # two-pass, tag-per-lane (forced for tiny batches too)
     _, blocks = _corpus_blocks(fixtures)
     blocks = blocks + H.synthetic_blocks(5150, 48)
     c1, s1 = compress_many(e1, blocks, 0)
@@ -327,7 +328,7 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     assert d2[:len(blocks)] == blocks
     d4, s4 = decompress_many(e4, items, caps)
     assert np.array_equal(s4, s2) and d4 == d2
-    for ex in (e3, e5):
+    for ex in (e3, e5, e6):
         dx, sx = decompress_many(ex, items, caps)
         assert np.array_equal(sx, s1) and dx == d1
     # ragged / tiny / unaligned inputs through the ring's head-tail byte path
@@ -335,6 +336,8 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     d4s, s4s = decompress_many(e4, small)
     d2s, s2s = decompress_many(e2, small)
     assert d4s == d2s and not s4s.any()
+    d6s, s6s = decompress_many(e6, small)
+    assert d6s == d2s and not s6s.any()
     # long literals at every source/destination alignment (the vectorised literal path of kernel 5)
     rng2 = np.random.default_rng(23)
     lits = []
@@ -342,7 +345,7 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
         for pad in (0, 1, 5, 15):
             raw = rng2.integers(0, 256, size=n + pad, dtype=np.uint8).tobytes()
             lits.append(oracle.compress(raw)[1])  # incompressible -> (pad-shifted) long literals
-    for ex in (e1, e3, e5):
+    for ex in (e1, e3, e5, e6):
         dl, sl = decompress_many(ex, lits)
         assert not sl.any() and dl == [oracle.decompress(c)[1] for c in lits]
     e1.close()
@@ -350,6 +353,37 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     e3.close()
     e4.close()
     e5.close()
+    e6.close()
+
+
+def test_v6_waves_work_stealing_and_fallback(oracle, fixtures):
+    """Kernel 6 with tiny waves (many scan/decode kernel pairs), thousands of ragged blocks sharing
+    16-byte output vectors with their neighbours, and blocks denser than the checkpoint budget
+    (handed to the v3 engine inside the decode kernel)."""
+    from snappier_b200.batch import decompress_many
+    e6 = _engine_with({"SNP_DECOMP_KERNEL": "6", "SNP_V6_MIN_ITEMS": "1", "SNP_V6_WAVE": "700"})
+    _, blocks = _corpus_blocks(fixtures)
+    blocks = blocks + H.synthetic_blocks(808, 60)
+    rng = np.random.default_rng(5)
+    raw = []
+    for i in range(2500):
+        b = blocks[i % len(blocks)]
+        lo = int(rng.integers(0, 30000))
+        raw.append(b[lo: lo + int(rng.integers(0, 35000))])
+    # > 24 576 tags in one block: alternating 1-byte literals and 4-byte copies (budget = 768 groups of 32)
+    dense = bytearray(oracle.varint_write(100000))
+    dense += bytes([3 << 2]) + b"abcd"
+    total = 4
+    while total + 5 <= 100000:
+        dense += bytes([0]) + b"x" + bytes([((4 - 1) << 2) | 2]) + (4).to_bytes(2, "little")
+        total += 5
+    dense += bytes([(100000 - total - 1) << 2]) + b"y" * (100000 - total)  # 1 byte left
+    items = [oracle.compress(r)[1] for r in raw] + [bytes(dense)]
+    got, st = decompress_many(e6, items)
+    assert not st.any()
+    assert got[:-1] == raw
+    assert got[-1] == oracle.decompress(bytes(dense))[1] and len(got[-1]) == 100000
+    e6.close()
 
 
 def test_single_call_api_is_thread_safe(oracle):
