@@ -8,18 +8,23 @@
 //   pass A  k_tagscan_v6   one THREAD per block walks the tag chain (SnappyDecompressor.cs:184-347
 //           is a serial dependency chain, so a thread is the natural unit), validates every tag in
 //           stream order (the block's final status is decided here) and drops a checkpoint
-//           (ip, op) every 32 tags.  Input reaches each lane through a 128-byte shared-memory slot
-//           that the warp refills with one coalesced load.
+//           (ip, op) every 32 tag slots.  Input reaches each lane through a 32-byte register window
+//           (16-byte vector loads, one vector ahead of the cursor).
 //   pass B  k_decode_v6    one WARP per block (the north star's decomposition).  Per super-step
-//           lane l re-parses the 32 tags behind checkpoint 32*j+l into shared memory (1024 tags in
-//           flight), then the warp executes the groups in stream order, ONE TAG PER LANE: 16-byte
-//           vector loads of the source (input stream, shared-memory output window, or the block's
-//           older output in global memory), a register funnel to the byte offset, byte stores into
-//           a sliding shared-memory OUTPUT WINDOW, which is flushed to HBM as aligned 16-byte
-//           vectors.  Tags whose source is produced inside the same group wait for the frontier
-//           (multi-round resolution; the first pending tag is always runnable).  Overlapping
-//           copies with offset < 16 (CopyHelpers.IncrementalCopy's pattern replication) and
-//           literals > 64 bytes take warp-cooperative paths.
+//           lane l re-parses the 32 slots behind checkpoint 32*j+l into 4-byte records in shared
+//           memory (1024 tags in flight), then the warp executes the groups in stream order, ONE
+//           TAG PER LANE: output offsets by a shuffle scan of the lengths, 16-byte vector loads of
+//           the source (input stream, shared-memory output window, or the block's older output in
+//           global memory), a register funnel to the byte offset, byte stores into a sliding
+//           shared-memory OUTPUT WINDOW, which is flushed to HBM as aligned 16-byte vectors.  Tags
+//           whose source is produced inside the same group wait for the frontier (multi-round
+//           resolution; the first pending tag is always runnable).  Overlapping copies with
+//           offset < 16 (CopyHelpers.IncrementalCopy's pattern replication) and literals > 64 bytes
+//           take warp-cooperative paths.
+//
+// Slots: a tag is one slot {len (7 bits) | literal (1) | copy offset or literal input offset (24)};
+// a literal > 64 bytes is a head slot (len 0) plus a slot holding its length << 8, never split
+// across two groups (an empty pad slot is inserted when it would be).
 //
 // Semantics: /root/reference/Snappier/Internal/SnappyDecompressor.cs:43-92,184-347,556-611,
 // identical to v1/v3/v5 and oracle/snappy_oracle.c (status precedence = stream order).
@@ -35,22 +40,68 @@
 
 namespace snp {
 
-#define SNP6_T 32u  // tags per checkpoint group (= lanes)
+#define SNP6_T 32u  // slots per checkpoint group (= lanes)
 #ifndef SNP6_CKB
-#define SNP6_CKB 768u  // checkpoint budget per block: 24 576 tags; denser blocks fall back to v5
+#define SNP6_CKB 768u  // checkpoint budget per block: 24 576 slots; denser blocks fall back to v3
 #endif
 #define SNP6_NT_FALLBACK 0xffffffffu
-#define SNP6_KEEP 1024u                             // bytes of history the output window keeps across a slide
-#define SNP6_SPAN 2048u                             // 32 tags x 64 bytes: most a sub-group can produce
-#define SNP6_WIN (SNP6_KEEP + SNP6_SPAN + 64u)      // window bytes
-#define SNP6_LIT 0x80000000u
-#define SNP6_SLOTW 33u  // words per pass-A input slot row (32 + 1 pad: conflict-free rows and columns)
+#define SNP6_KEEP 768u                          // bytes of history the output window keeps across a slide
+#define SNP6_SPAN 2048u                         // 32 tags x 64 bytes: most a sub-group can produce
+#define SNP6_WIN (SNP6_KEEP + SNP6_SPAN + 64u)  // window bytes
+#define SNP6_FLUSH 512u                         // flush the window when this many bytes are pending
+#define SNP6_RLIT 0x80u
+#define SNP6_VMAX 0x1000000u  // record values (copy offsets, literal input offsets) are 24-bit
 
 struct alignas(16) V6Smem {  // pass B, per warp
-    uint32_t dst[32 * 33];   // [group lane][tag] output offset; entry [cnt] = end of the group
-    uint32_t src[32 * 33];   // literal: SNP6_LIT | input offset of the first byte; copy: offset
+    uint32_t rec[32 * 33];   // [group lane][slot] records
+    uint32_t gop[32];        // output offset at the start of each group
     uint8_t win[SNP6_WIN + 16];
+    uint4 pslot[32 * 3];     // parse: per-lane 32-byte input ring (48-byte pitch)
 };
+
+#ifdef SNP_EMU
+struct V6Stats {
+    unsigned long groups, subgroups, rounds, trips, ctags, huge, slides, tags, flushes, fast;
+};
+inline V6Stats &v6_stats() {
+    static V6Stats s{};
+    return s;
+}
+#define SNP6_STAT(f, n) do { if (lane_id() == 0) v6_stats().f += (n); } while (0)
+#else
+#define SNP6_STAT(f, n) do { } while (0)
+#endif
+
+// ---- explicit address-space accesses (the block functions are not inlined into the kernels, so
+//      plain pointers would compile to generic LD/ST) ------------------------------------------------
+#ifdef SNP_EMU
+__device__ __forceinline__ uint4 ldg_nc_v4(const uint4 *p) { return *p; }
+__device__ __forceinline__ uint4 ldg_v4(const uint4 *p) { return *p; }
+__device__ __forceinline__ void stg_v4(uint4 *p, uint4 v) { *p = v; }
+// stores the low min(m, 4) bytes of r at p
+__device__ __forceinline__ void st_win_bytes4(uint8_t *p, uint32_t r, uint32_t m) {
+    for (uint32_t j = 0; j < 4 && j < m; j++) p[j] = (uint8_t)(r >> (8 * j));
+}
+#else
+__device__ __forceinline__ uint4 ldg_nc_v4(const uint4 *p) { return __ldg(p); }
+__device__ __forceinline__ uint4 ldg_v4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void stg_v4(uint4 *p, uint4 v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_win_bytes4(uint8_t *p, uint32_t r, uint32_t m) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile(
+        "{\n\t.reg .pred p0,p1,p2,p3;\n\t.reg .b32 t1,t2,t3;\n\t"
+        "setp.gt.u32 p0,%2,0;\n\tsetp.gt.u32 p1,%2,1;\n\tsetp.gt.u32 p2,%2,2;\n\tsetp.gt.u32 p3,%2,3;\n\t"
+        "shr.u32 t1,%1,8;\n\tshr.u32 t2,%1,16;\n\tshr.u32 t3,%1,24;\n\t"
+        "@p0 st.shared.u8 [%0],%1;\n\t@p1 st.shared.u8 [%0+1],t1;\n\t"
+        "@p2 st.shared.u8 [%0+2],t2;\n\t@p3 st.shared.u8 [%0+3],t3;\n\t}" ::"r"(sa), "r"(r), "r"(m) : "memory");
+}
+#endif
 
 struct Tag6 {
     uint32_t hdr, take, off;
@@ -86,123 +137,123 @@ struct Scan6Args {
     int32_t *status;
     size_t first_item, n_items;  // this wave: items [first_item, first_item + n_items)
     unsigned long long *next_item;
-    uint32_t *ntags;  // per wave slot: tag count, or SNP6_NT_FALLBACK
+    uint32_t *ntags;  // per wave slot: slot count, or SNP6_NT_FALLBACK
     uint2 *ck;        // per wave slot: SNP6_CKB checkpoints (ip, op)
 };
 
-// One warp of the persistent scan: every lane owns one block at a time and fetches the next one
-// when it is done.  `slots` = 32 rows of SNP6_SLOTW words of shared memory.
-__device__ __forceinline__ void tagscan_warp_v6(const Scan6Args &a, const uint32_t *lut, uint32_t *slots) {
-    const unsigned lane = lane_id();
-    bool have = false, exhausted = false;
+// Per-lane 32-byte register window over the lane's own input stream: c holds the 16-byte vector
+// under the cursor, n the next one (loaded when the cursor enters c, i.e. one vector ahead).
+struct InWin6 {
+    const uint4 *base;  // 16-byte aligned; stream byte p sits at byte (skew + p)
+    uint32_t last_v;    // last vector index that may be read
+    uint32_t vb;        // vector index held in c (n holds vb + 1)
+    bool valid;
+    uint4 c, n;
+    __device__ __forceinline__ void words(uint32_t wi, uint32_t &w0, uint32_t &w1) {
+        const uint32_t vq = wi >> 2;
+        if (!valid || vq != vb) {
+            if (valid && vq == vb + 1) c = n;
+            else c = ldg_nc_v4(base + min(vq, last_v));
+            n = ldg_nc_v4(base + min(vq + 1, last_v));
+            vb = vq;
+            valid = true;
+        }
+        const unsigned sel = wi & 3;
+        w0 = sel == 0 ? c.x : sel == 1 ? c.y : sel == 2 ? c.z : c.w;
+        w1 = sel == 0 ? c.y : sel == 1 ? c.z : sel == 2 ? c.w : n.x;
+    }
+};
+
+// The persistent scan: every THREAD owns one block at a time, walks its tag chain and fetches the
+// next block when it is done (a flat state machine, so lanes of a warp never wait for each other's
+// blocks).  No shared memory, no collectives: the stream reaches the lane through InWin6.
+__device__ __forceinline__ void tagscan_thread_v6(const Scan6Args &a, const uint32_t *lut) {
+    bool have = false;
     size_t slot_idx = 0, item = 0;
-    const uint32_t *in_w = nullptr;
-    uint32_t skew = 0, n_in = 0, last_w = 0, U = 0, ip = 0, op = 0, ntag = 0, sbyte = 0;
-    bool svalid = false;
-    int st = SNP_OK;
-    uint32_t *myslot = slots + lane * SNP6_SLOTW;
-
+    uint32_t ski = 0, n_in = 0, U = 0, ip = 0, op = 0, nslot = 0;
+    InWin6 w;
+    w.base = nullptr;
+    w.last_v = 0;
+    w.vb = 0;
+    w.valid = false;
     for (;;) {
-        if (!have && !exhausted) {
+        if (!have) {
             const unsigned long long it = atomicAdd(a.next_item, 1ull);
-            if (it >= a.n_items) {
-                exhausted = true;
-            } else {
-                slot_idx = (size_t)it;
-                item = a.first_item + slot_idx;
-                const uint8_t *in = a.in_base + a.in_off[item];
-                n_in = a.in_len[item];
-                const uint32_t cap = a.out_cap[item];
-                if (n_in >= 0x7fff0000u) {  // 32-bit stream offsets need headroom: v1 walker in pass B
-                    a.ntags[slot_idx] = SNP6_NT_FALLBACK;
-                } else {
-                    uint32_t used;
-                    st = varint_read(in, n_in, &U, &used);  // SnappyDecompressor.cs:50-63
-                    if (st == SNP_OK && U > 0x7fffffffu) st = SNP_INVALID_LENGTH;
-                    if (st == SNP_OK && cap < U) st = SNP_OUTPUT_TOO_SMALL;
-                    if (st != SNP_OK || U == 0) {
-                        a.out_len[item] = 0;
-                        a.status[item] = st;
-                        a.ntags[slot_idx] = 0;
-                    } else {
-                        skew = (uint32_t)((uintptr_t)in & 3);
-                        in_w = (const uint32_t *)((uintptr_t)in - skew);
-                        last_w = (skew + n_in - 1) >> 2;
-                        ip = used;
-                        op = 0;
-                        ntag = 0;
-                        svalid = false;
-                        have = true;
-                    }
-                }
+            if (it >= a.n_items) return;
+            slot_idx = (size_t)it;
+            item = a.first_item + slot_idx;
+            const uint8_t *in = a.in_base + a.in_off[item];
+            n_in = a.in_len[item];
+            const uint32_t cap = a.out_cap[item];
+            if (n_in >= SNP6_VMAX) {  // records hold 24-bit input offsets: v3 / v1 walker in pass B
+                a.ntags[slot_idx] = SNP6_NT_FALLBACK;
+                continue;
             }
-        }
-        if (__all_sync(SNP_FULL, exhausted && !have)) break;
-
-        // ---- refill: the warp loads 128 bytes for every lane whose slot ran out ------------
-        const uint32_t pos0 = skew + ip;
-        const bool need = have && (!svalid || pos0 - sbyte > 123u);
-        unsigned m = __ballot_sync(SNP_FULL, need);
-        __syncwarp();  // every lane is done reading the slots it is about to see overwritten
-        while (m) {
-            const unsigned b = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t w0 = __shfl_sync(SNP_FULL, pos0 >> 2, b);
-            const uint32_t lw = __shfl_sync(SNP_FULL, last_w, b);
-            const unsigned long long base = __shfl_sync(SNP_FULL, (unsigned long long)(uintptr_t)in_w, b);
-            slots[b * SNP6_SLOTW + lane] = ((const uint32_t *)(uintptr_t)base)[min(w0 + lane, lw)];
-        }
-        if (need) {
-            sbyte = pos0 & ~3u;
-            svalid = true;
-        }
-        __syncwarp();
-
-        // ---- up to 4 tags per lane from the slot ---------------------------------------------
-#pragma unroll 1
-        for (int r = 0; r < 4; r++) {
-            if (!have) break;
-            if (ip >= n_in) {
-                have = false;
-            } else {
-                const uint32_t rel = skew + ip - sbyte;
-                if (rel > 123u) break;  // next refill
-                const unsigned sh = (rel & 3) * 8;
-                const uint32_t w0 = myslot[rel >> 2], w1 = myslot[(rel >> 2) + 1];
-                const uint32_t v = __funnelshift_r(w0, w1, sh);
-                const Tag6 t = decode_tag6(v, w1 >> sh, lut[v & 0xff], n_in - ip);
-                if (t.end) {
-                    have = false;
-                } else if (!t.is_lit && t.off - 1u >= op) {  // off == 0 || off > produced (:598-601)
-                    st = SNP_INVALID_COPY_OFFSET;
-                    have = false;
-                } else if (t.take > U - op) {  // :570-573, :603-606
-                    st = SNP_DATA_TOO_LONG;
-                    have = false;
-                } else {
-                    if (t.take) {
-                        if ((ntag & (SNP6_T - 1)) == 0) {
-                            const uint32_t g = ntag / SNP6_T;
-                            if (g >= SNP6_CKB) {  // denser than the checkpoint budget: pass B decodes it with v5
-                                a.ntags[slot_idx] = SNP6_NT_FALLBACK;
-                                have = false;
-                                break;
-                            }
-                            a.ck[slot_idx * SNP6_CKB + g] = make_uint2(ip, op);
-                        }
-                        ntag++;
-                    }
-                    op += t.take;
-                    ip += t.hdr + (t.is_lit ? t.take : 0u);
-                    if (t.partial) have = false;
-                }
-            }
-            if (!have) {  // the stream ended or failed: this is the block's result
-                if (st == SNP_OK && op < U) st = SNP_INCOMPLETE;  // Snappy.cs:178-181
-                a.out_len[item] = st == SNP_OK ? op : 0u;
+            uint32_t used;
+            int st = varint_read(in, n_in, &U, &used);  // SnappyDecompressor.cs:50-63
+            if (st == SNP_OK && U > 0x7fffffffu) st = SNP_INVALID_LENGTH;
+            if (st == SNP_OK && cap < U) st = SNP_OUTPUT_TOO_SMALL;
+            if (st != SNP_OK || U == 0) {
+                a.out_len[item] = 0;
                 a.status[item] = st;
-                a.ntags[slot_idx] = st == SNP_OK ? ntag : 0u;
+                a.ntags[slot_idx] = 0;
+                continue;
             }
+            ski = (uint32_t)((uintptr_t)in & 15);
+            w.base = (const uint4 *)((uintptr_t)in - ski);
+            w.last_v = (ski + n_in - 1) >> 4;
+            w.valid = false;
+            ip = used;
+            op = 0;
+            nslot = 0;
+            have = true;
+        }
+        // ---- one tag ----------------------------------------------------------------------------
+        int st = SNP_OK;
+        bool done = false;
+        if (ip >= n_in) {
+            done = true;
+        } else {
+            const uint32_t pos = ski + ip;
+            uint32_t w0, w1;
+            w.words(pos >> 2, w0, w1);
+            const unsigned sh = (pos & 3) * 8;
+            const uint32_t v = __funnelshift_r(w0, w1, sh);
+            const Tag6 t = decode_tag6(v, w1 >> sh, lut[v & 0xff], n_in - ip);
+            if (t.end) {
+                done = true;
+            } else if (!t.is_lit && t.off - 1u >= op) {  // off == 0 || off > produced (:598-601)
+                st = SNP_INVALID_COPY_OFFSET;
+                done = true;
+            } else if (t.take > U - op) {  // :570-573, :603-606
+                st = SNP_DATA_TOO_LONG;
+                done = true;
+            } else {
+                if (t.take) {
+                    const bool huge = t.take > 64u;  // literals only
+                    if (huge && (nslot & (SNP6_T - 1)) == SNP6_T - 1) nslot++;  // pad: head + length stay together
+                    const bool wide = !t.is_lit && t.off >= SNP6_VMAX;          // a 32-bit copy offset
+                    const uint32_t g = nslot / SNP6_T;
+                    if (wide || g >= SNP6_CKB) {
+                        // outside the record format / denser than the checkpoint budget: v3 engine in pass B
+                        a.ntags[slot_idx] = SNP6_NT_FALLBACK;
+                        have = false;
+                        continue;
+                    }
+                    if ((nslot & (SNP6_T - 1)) == 0) a.ck[slot_idx * SNP6_CKB + g] = make_uint2(ip, op);
+                    nslot += huge ? 2u : 1u;
+                }
+                op += t.take;
+                ip += t.hdr + (t.is_lit ? t.take : 0u);
+                done = t.partial;
+            }
+        }
+        if (done) {  // the stream ended or failed: this is the block's result
+            if (st == SNP_OK && op < U) st = SNP_INCOMPLETE;  // Snappy.cs:178-181
+            a.out_len[item] = st == SNP_OK ? op : 0u;
+            a.status[item] = st;
+            a.ntags[slot_idx] = st == SNP_OK ? nslot : 0u;
+            have = false;
         }
     }
 }
@@ -227,14 +278,14 @@ __device__ __forceinline__ void copy_wide_v6(const uint8_t *s, uint8_t *d, uint3
     const uint4 *last = (const uint4 *)(((uintptr_t)in_end - 1) & ~(uintptr_t)15);
     const unsigned ws = sb >> 2, bs = (sb & 3) * 8;
     for (uint32_t v = lane; v < nvec; v += SNP_WARP) {
-        const uint4 A = base[v];
+        const uint4 A = ldg_nc_v4(base + v);
         const uint4 *pb = base + v + 1;
-        const uint4 B = *(pb <= last ? pb : last);
+        const uint4 B = ldg_nc_v4(pb <= last ? pb : last);
         uint32_t x0 = A.x, x1 = A.y, x2 = A.z, x3 = A.w, x4 = B.x, x5 = B.y, x6 = B.z;
         if (ws & 2) x0 = x2, x1 = x3, x2 = x4, x3 = x5, x4 = x6;
         if (ws & 1) x0 = x1, x1 = x2, x2 = x3, x3 = x4, x4 = (ws & 2) ? B.w : x5;
-        dv[v] = make_uint4(__funnelshift_r(x0, x1, bs), __funnelshift_r(x1, x2, bs), __funnelshift_r(x2, x3, bs),
-                           __funnelshift_r(x3, x4, bs));
+        stg_v4(dv + v, make_uint4(__funnelshift_r(x0, x1, bs), __funnelshift_r(x1, x2, bs),
+                                  __funnelshift_r(x2, x3, bs), __funnelshift_r(x3, x4, bs)));
     }
     const uint32_t done = head + (nvec << 4);
     if (done + lane < len) d[done + lane] = s[done + lane];
@@ -253,29 +304,7 @@ __device__ __forceinline__ void funnel16(const uint4 &A, const uint4 &B, unsigne
     r3 = __funnelshift_r(x3, x4, bs);
 }
 
-// Per-lane 32-byte register window over the lane's own part of the input stream (pass B parse).
-struct InWin6 {
-    const uint4 *base;  // 16-byte aligned; stream byte p sits at byte (skew + p)
-    uint32_t last_v;    // last vector index that may be read
-    uint32_t vb;        // vector index held in c (n holds vb + 1)
-    bool valid;
-    uint4 c, n;
-    __device__ __forceinline__ void words(uint32_t wi, uint32_t &w0, uint32_t &w1) {
-        const uint32_t vq = wi >> 2;
-        if (!valid || vq != vb) {
-            if (valid && vq == vb + 1) c = n;
-            else c = base[min(vq, last_v)];
-            n = base[min(vq + 1, last_v)];
-            vb = vq;
-            valid = true;
-        }
-        const unsigned sel = wi & 3;
-        w0 = sel == 0 ? c.x : sel == 1 ? c.y : sel == 2 ? c.z : c.w;
-        w1 = sel == 0 ? c.y : sel == 1 ? c.z : sel == 2 ? c.w : n.x;
-    }
-};
-
-// Decodes one block whose tag stream pass A validated (status OK, nt tags, checkpoints ck[]).
+// Decodes one block whose tag stream pass A validated (status OK, nt slots, checkpoints ck[]).
 __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, uint8_t *out, uint32_t U,
                                              uint32_t nt, const uint2 *ck, const uint32_t *lut, V6Smem *sm) {
     const unsigned lane = lane_id();
@@ -287,78 +316,123 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
     const uint32_t sko = (uint32_t)((uintptr_t)out & 15);
     uint8_t *outA = out - sko;
     const uint4 *win_v = (const uint4 *)sm->win;
-    uint32_t wbase = 0;       // P of win[0] (multiple of 16)
-    uint32_t hstart = sko;    // window holds valid bytes for P in [hstart, produced)
-    uint32_t flushed = sko;   // every byte of P < flushed is in global memory
+    uint32_t wbase = 0;      // P of win[0] (multiple of 16)
+    uint32_t hstart = sko;   // window holds valid bytes for P in [hstart, produced)
+    uint32_t flushed = sko;  // every byte of P < flushed is in global memory
     const uint32_t G = (nt + SNP6_T - 1) / SNP6_T;
 
+    // writes window bytes P in [flushed, upto & ~15) to global memory as aligned vectors
+    auto flush_to = [&](uint32_t upto) {
+        const uint32_t fl1 = upto & ~15u;
+        if (fl1 > flushed) {
+            SNP6_STAT(flushes, 1);
+            uint32_t fl0 = flushed & ~15u;
+            if (fl0 < sko) {  // first vector of a block whose output is not 16-byte aligned (wbase == 0 here)
+                if (lane >= sko && lane < 16u) outA[lane] = sm->win[lane];
+                fl0 = 16;
+            }
+#pragma unroll 1
+            for (uint32_t v = (fl0 >> 4) + lane; v < (fl1 >> 4); v += SNP_WARP)
+                stg_v4((uint4 *)outA + v, win_v[v - (wbase >> 4)]);
+            flushed = fl1;
+        }
+    };
+
+#pragma unroll 1
     for (uint32_t g0 = 0; g0 < G; g0 += 32) {
-        // ================= parse: lane l decodes the tags of group g0 + l into shared memory ===
+        // ================= parse: lane l decodes the slots of group g0 + l into shared memory ===
         {
             const uint32_t my_g = g0 + lane;
-            const bool has = my_g < G;
             uint32_t ip = 0, op = 0, cnt = 0;
-            if (has) {
+            if (my_g < G) {
                 const uint2 c = ck[my_g];
                 ip = c.x;
                 op = c.y;
                 cnt = min(SNP6_T, nt - SNP6_T * my_g);
+                sm->gop[lane] = op;
             }
-            InWin6 w;
-            w.base = in_v;
-            w.last_v = in_last_v;
-            w.vb = 0;
-            w.valid = false;
-            const uint32_t kmax = min(SNP6_T, nt - SNP6_T * g0);  // lane 0 has the most tags
+            uint32_t *myrec = sm->rec + lane * 33;
+            uint4 *ring = sm->pslot + lane * 3;  // two 16-byte vectors: vector v lives in ring[v & 1]
+            uint32_t vhave = 0xfffffff0u;        // highest vector index loaded so far
+            const uint32_t kmax = min(SNP6_T, nt - SNP6_T * g0);  // the first group of the step is the fullest
+            uint32_t k = 0;
 #pragma unroll 1
-            for (uint32_t k = 0; k < kmax; k++) {
+            for (uint32_t iter = 0; iter < kmax; iter++) {
                 if (k < cnt) {
                     const uint32_t pos = ski + ip;
-                    uint32_t w0, w1;
-                    w.words(pos >> 2, w0, w1);
+                    const uint32_t v0 = pos >> 4, v1 = (pos + 4) >> 4;  // vectors holding bytes pos .. pos+4
+                    if (v1 != vhave) {  // (re)fill: vector v lives in ring[v & 1]
+                        if (v0 != v1 && v0 != vhave) ring[v0 & 1] = ldg_nc_v4(in_v + min(v0, in_last_v));
+                        ring[v1 & 1] = ldg_nc_v4(in_v + min(v1, in_last_v));
+                        vhave = v1;
+                    }
+                    const volatile uint32_t *rw = (const volatile uint32_t *)ring;
+                    const uint32_t wi = pos >> 2;
+                    const uint32_t w0 = rw[wi & 7], w1 = rw[(wi + 1) & 7];
                     const unsigned sh = (pos & 3) * 8;
                     const uint32_t v = __funnelshift_r(w0, w1, sh);
                     const Tag6 t = decode_tag6(v, w1 >> sh, lut[v & 0xff], n_in - ip);
-                    sm->dst[lane * 33 + k] = op;
-                    sm->src[lane * 33 + k] = t.is_lit ? (SNP6_LIT | (ip + t.hdr)) : t.off;
-                    op += t.take;
-                    ip += t.hdr + (t.is_lit ? t.take : 0u);
+                    const bool huge = t.take > 64u;
+                    if (huge && k == SNP6_T - 1) {
+                        myrec[k] = 0;  // pad: the literal opens the next group
+                        k = SNP6_T;
+                    } else {
+                        myrec[k] = (huge ? 0u : t.take) | (t.is_lit ? (SNP6_RLIT | ((ip + t.hdr) << 8)) : (t.off << 8));
+                        if (huge) myrec[k + 1] = t.take << 8;  // low byte 0: neither a tag nor a head
+                        k += huge ? 2u : 1u;
+                        op += t.take;
+                        ip += t.hdr + (t.is_lit ? t.take : 0u);
+                    }
                 }
             }
-            if (has) sm->dst[lane * 33 + cnt] = op;
         }
         __syncwarp();
 
-        // ================= execute the groups in stream order, one tag per lane ==================
+        // ================= execute the groups in stream order, one slot per lane ==================
         const uint32_t nb = min(32u, G - g0);
 #pragma unroll 1
         for (uint32_t b = 0; b < nb; b++) {
             const uint32_t cntb = min(SNP6_T, nt - SNP6_T * (g0 + b));
+            SNP6_STAT(groups, 1);
+            SNP6_STAT(tags, cntb);
             const bool valid = lane < cntb;
-            uint32_t d = 0, e = 0, sr = 0;
-            if (valid) {
-                d = sm->dst[b * 33 + lane] + sko;
-                e = sm->dst[b * 33 + lane + 1] + sko;
-                sr = sm->src[b * 33 + lane];
+            const uint32_t r = valid ? sm->rec[b * 33 + lane] : 0u;
+            const uint32_t gbase = sm->gop[b] + sko;
+            const bool head = (r & 0xffu) == SNP6_RLIT;  // literal > 64 bytes: its length is in the next slot
+            const unsigned hm = __ballot_sync(SNP_FULL, head);
+            uint32_t len = r & 0x7fu;  // 0 for heads, length slots and pads
+            if (hm) {
+                const uint32_t nxt = __shfl_down_sync(SNP_FULL, r, 1);
+                if (head) len = nxt >> 8;
             }
-            const uint32_t len = e - d;
-            const bool is_lit = (sr & SNP6_LIT) != 0;
-            const uint32_t off = sr;                  // copies
-            const uint32_t lsrc = sr & ~SNP6_LIT;     // literals: input offset
-            unsigned hm = __ballot_sync(SNP_FULL, valid && len > 64u);  // literals beyond the tag-per-lane path
+            const bool is_lit = (r & SNP6_RLIT) != 0;
+            const uint32_t val = r >> 8;  // copy offset / literal input offset
+            // output offsets: inclusive scan of the lengths
+            uint32_t incl = len;
+#pragma unroll
+            for (int dlt = 1; dlt < SNP_WARP; dlt <<= 1) {
+                const uint32_t y = __shfl_up_sync(SNP_FULL, incl, dlt);
+                if (lane >= (unsigned)dlt) incl += y;
+            }
+            const uint32_t e = gbase + incl, d = e - len;
+            unsigned hleft = hm;
             uint32_t t0 = 0;
             for (;;) {
-                const uint32_t t1 = hm ? (uint32_t)(__ffs(hm) - 1) : cntb;
+                const uint32_t t1 = hleft ? (uint32_t)(__ffs(hleft) - 1) : cntb;
                 if (t1 > t0) {
                     // ------------- sub-group [t0, t1): every tag <= 64 bytes ---------------------
+                    SNP6_STAT(subgroups, 1);
                     const uint32_t ss = __shfl_sync(SNP_FULL, d, t0);
                     const uint32_t se = __shfl_sync(SNP_FULL, e, t1 - 1);
                     if (se > wbase + SNP6_WIN) {  // slide the window: keep SNP6_KEEP bytes of history
+                        flush_to(ss);
                         uint32_t nbse = ss > SNP6_KEEP ? ss - SNP6_KEEP : 0u;
                         nbse = max(nbse, hstart) & ~15u;
                         if (nbse > wbase) {
+                            SNP6_STAT(slides, 1);
                             const uint32_t shv = (nbse - wbase) >> 4;
                             const uint32_t nvec = (ss - nbse + 15) >> 4;
+#pragma unroll 1
                             for (uint32_t v0 = 0; v0 < nvec; v0 += SNP_WARP) {
                                 const uint32_t v = v0 + lane;
                                 uint4 x = make_uint4(0, 0, 0, 0);
@@ -371,66 +445,53 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                             hstart = max(hstart, nbse);
                         }
                     }
-                    const bool mine = valid && lane >= t0 && lane < t1;
-                    const uint32_t s_pos = d - off;  // copies: P of the first source byte
+                    const bool mine = valid && lane >= t0 && lane < t1 && len != 0;
+                    const uint32_t s_pos = d - val;  // copies: P of the first source byte
                     const uint32_t s_end = s_pos + len;
-                    const bool ctype = mine && !is_lit && off < 16u && len > off;  // pattern replication
-                    unsigned pending = (t1 >= 32 ? 0xffffffffu : ((1u << t1) - 1u)) & ~((1u << t0) - 1u);
+                    const bool ctype = mine && !is_lit && val < 16u && len > val;  // pattern replication
+                    const bool dep = mine && !is_lit && s_end > ss;                // source produced inside this sub-group
+                    unsigned pending = __ballot_sync(SNP_FULL, mine);
+                    const bool fast = __ballot_sync(SNP_FULL, dep) == 0;  // no in-group dependency: one round, no frontier
+                    SNP6_STAT(fast, fast ? 1 : 0);
                     while (pending) {
-                        const unsigned f = __ffs(pending) - 1;
-                        const uint32_t F = __shfl_sync(SNP_FULL, d, f);  // every byte below F is final
-                        const bool ready =
-                            mine && ((pending >> lane) & 1u) && (is_lit || s_end <= F || lane == f);
+                        SNP6_STAT(rounds, 1);
+                        bool ready = mine;
+                        if (!fast) {
+                            const unsigned f = __ffs(pending) - 1;
+                            const uint32_t F = __shfl_sync(SNP_FULL, d, f);  // every byte below F is final
+                            ready = mine && ((pending >> lane) & 1u) && (is_lit || s_end <= F || lane == f);
+                        }
                         // ---- (S) one tag per lane, 16 bytes per trip --------------------------------
                         {
                             uint32_t rem = (ready && !ctype) ? len : 0u;
-                            uint32_t cd = d;
-                            uint32_t cs = is_lit ? ski + lsrc : s_pos;
+                            uint32_t cd = d - wbase;  // window offset of the next byte to write
+                            uint32_t cs = is_lit ? ski + val : s_pos;
                             while (__any_sync(SNP_FULL, rem != 0)) {
+                                SNP6_STAT(trips, 1);
                                 const uint32_t m = min(rem, 16u);
                                 uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
                                 if (m) {
                                     const unsigned sh = cs & 15u;
-                                    const bool need_b = sh + m > 16u;
-                                    uint4 A, B;
+                                    uint4 A, B = make_uint4(0, 0, 0, 0);
                                     if (!is_lit && cs >= hstart) {  // recent output: shared-memory window
                                         const uint32_t vi = (cs - wbase) >> 4;
                                         A = win_v[vi];
                                         B = win_v[vi + 1];
-                                    } else {  // input stream, or output older than the window
-                                        const uint4 *gp = is_lit ? in_v : (const uint4 *)outA;
-                                        A = gp[cs >> 4];
-                                        B = A;
-                                        if (need_b) B = gp[(cs >> 4) + 1];
+                                    } else if (is_lit) {  // input stream
+                                        A = ldg_nc_v4(in_v + (cs >> 4));
+                                        if (sh + m > 16u) B = ldg_nc_v4(in_v + (cs >> 4) + 1);
+                                    } else {  // output older than the window: flushed long ago
+                                        A = ldg_v4((const uint4 *)outA + (cs >> 4));
+                                        if (sh + m > 16u) B = ldg_v4((const uint4 *)outA + (cs >> 4) + 1);
                                     }
                                     funnel16(A, B, sh, r0, r1, r2, r3);
                                 }
                                 const uint32_t mx = __reduce_max_sync(SNP_FULL, m);
-                                uint8_t *wp = sm->win + (cd - wbase);
-                                if (mx > 0) {
-                                    if (m > 0) wp[0] = (uint8_t)r0;
-                                    if (m > 1) wp[1] = (uint8_t)(r0 >> 8);
-                                    if (m > 2) wp[2] = (uint8_t)(r0 >> 16);
-                                    if (m > 3) wp[3] = (uint8_t)(r0 >> 24);
-                                }
-                                if (mx > 4) {
-                                    if (m > 4) wp[4] = (uint8_t)r1;
-                                    if (m > 5) wp[5] = (uint8_t)(r1 >> 8);
-                                    if (m > 6) wp[6] = (uint8_t)(r1 >> 16);
-                                    if (m > 7) wp[7] = (uint8_t)(r1 >> 24);
-                                }
-                                if (mx > 8) {
-                                    if (m > 8) wp[8] = (uint8_t)r2;
-                                    if (m > 9) wp[9] = (uint8_t)(r2 >> 8);
-                                    if (m > 10) wp[10] = (uint8_t)(r2 >> 16);
-                                    if (m > 11) wp[11] = (uint8_t)(r2 >> 24);
-                                }
-                                if (mx > 12) {
-                                    if (m > 12) wp[12] = (uint8_t)r3;
-                                    if (m > 13) wp[13] = (uint8_t)(r3 >> 8);
-                                    if (m > 14) wp[14] = (uint8_t)(r3 >> 16);
-                                    if (m > 15) wp[15] = (uint8_t)(r3 >> 24);
-                                }
+                                uint8_t *wp = sm->win + cd;
+                                st_win_bytes4(wp, r0, m);
+                                if (mx > 4) st_win_bytes4(wp + 4, r1, m > 4 ? m - 4 : 0u);
+                                if (mx > 8) st_win_bytes4(wp + 8, r2, m > 8 ? m - 8 : 0u);
+                                if (mx > 12) st_win_bytes4(wp + 12, r3, m > 12 ? m - 12 : 0u);
                                 cs += 16;
                                 cd += 16;
                                 rem -= m;
@@ -439,40 +500,29 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                         // ---- (C) overlapping copies with offset < 16: the warp replicates the pattern
                         unsigned cm = __ballot_sync(SNP_FULL, ready && ctype);
                         while (cm) {
+                            SNP6_STAT(ctags, 1);
                             const unsigned i = __ffs(cm) - 1;
                             cm &= cm - 1;
                             const uint32_t dd = __shfl_sync(SNP_FULL, d, i);
                             const uint32_t ll = __shfl_sync(SNP_FULL, len, i);
-                            const uint32_t oo = __shfl_sync(SNP_FULL, off, i);
+                            const uint32_t oo = __shfl_sync(SNP_FULL, val, i);
                             const uint32_t sp = dd - oo;  // pattern = P in [sp, dd), final since dd == F
                             const uint8_t *pat = sp >= hstart ? sm->win + (sp - wbase) : outA + sp;
                             for (uint32_t k = lane; k < ll; k += SNP_WARP) sm->win[dd - wbase + k] = pat[k % oo];
                         }
-                        __syncwarp();  // this round's window bytes are visible to the next round
+                        __syncwarp();  // this round's window bytes are visible to the next round / the flush
                         pending &= ~__ballot_sync(SNP_FULL, ready);
                     }
-                    // ------------- flush the finished 16-byte vectors of the window to HBM -----
-                    {
-                        const uint32_t fl1 = se & ~15u;
-                        if (fl1 > flushed) {
-                            uint32_t fl0 = flushed & ~15u;
-                            if (fl0 < sko) {  // first vector of a block whose output is not 16-byte aligned
-                                if (lane >= sko && lane < 16u) outA[lane] = sm->win[lane];
-                                fl0 = 16;
-                            }
-                            for (uint32_t v = (fl0 >> 4) + lane; v < (fl1 >> 4); v += SNP_WARP)
-                                ((uint4 *)outA)[v] = win_v[v - (wbase >> 4)];
-                            flushed = fl1;
-                        }
-                        __syncwarp();
-                    }
+                    if (se - flushed >= SNP6_FLUSH) flush_to(se);
                 }
                 if (t1 >= cntb) break;
                 // ------------- literal > 64 bytes: straight from the input to HBM -------------------
                 {
+                    SNP6_STAT(huge, 1);
                     const uint32_t dd = __shfl_sync(SNP_FULL, d, t1);
                     const uint32_t ll = __shfl_sync(SNP_FULL, len, t1);
-                    const uint32_t ls = __shfl_sync(SNP_FULL, lsrc, t1);
+                    const uint32_t ls = __shfl_sync(SNP_FULL, val, t1);
+                    flush_to(dd);
                     if (dd > flushed) {  // < 16 pending tail bytes of the window
                         const uint32_t n = dd - flushed;
                         if (lane < n) outA[flushed + lane] = sm->win[flushed - wbase + lane];
@@ -489,14 +539,15 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                     for (uint32_t k = lane; k < keep; k += SNP_WARP) sm->win[hstart - wbase + k] = tail[k];
                     __syncwarp();
                 }
-                hm &= hm - 1;
-                t0 = t1 + 1;
+                hleft &= hleft - 1;
+                t0 = t1 + 2;  // skip the head and its length slot
             }
         }
-        __syncwarp();  // the next super-step's parse overwrites the tag records
+        __syncwarp();  // the next super-step's parse overwrites the records
     }
-    // ---- tail: the bytes behind the last full vector ------------------------------------------
+    // ---- tail: everything still in the window ------------------------------------------------------
     const uint32_t endP = U + sko;
+    flush_to(endP);
     if (endP > flushed) {
         const uint32_t n = endP - flushed;
         for (uint32_t k = lane; k < n; k += SNP_WARP) outA[flushed + k] = sm->win[flushed - wbase + k];
@@ -520,17 +571,12 @@ struct Decode6Args {
 };
 
 #ifdef SNP_EMU
-// the emulator has no v5/v1 engines: the harness reports blocks that would take them
+// the emulator has no v3/v1 engines: the harness reports blocks that would take them
 int v6_emu_fallback(const uint8_t *in, uint32_t n_in, uint8_t *out, uint32_t cap, uint32_t *written);
 #endif
 
-// One warp of the persistent decode kernel.  `q` (v5's tag queue) is only used by the fallback.
-__device__ __forceinline__ void decode_warp_v6(const Decode6Args &a, const uint32_t *lut, V6Smem *sm
-#ifndef SNP_EMU
-                                               ,
-                                               WarpQueue3 *q
-#endif
-) {
+// One warp of the persistent decode kernel.
+__device__ __forceinline__ void decode_warp_v6(const Decode6Args &a, const uint32_t *lut, V6Smem *sm) {
     const unsigned lane = lane_id();
     for (;;) {
         unsigned long long it = 0;
@@ -550,8 +596,8 @@ __device__ __forceinline__ void decode_warp_v6(const Decode6Args &a, const uint3
 #else
             if (n_in >= 0x7fff0000u) {
                 st = decompress_block_v1(in, n_in, out, a.out_cap[item], &w);
-            } else {
-                st = decompress_block_v3(in, n_in, out, a.out_cap[item], &w, lut, q);
+            } else {  // v3's tag queue borrows the record area
+                st = decompress_block_v3(in, n_in, out, a.out_cap[item], &w, lut, (WarpQueue3 *)sm->rec);
             }
 #endif
             if (lane == 0) {
@@ -569,31 +615,29 @@ __device__ __forceinline__ void decode_warp_v6(const Decode6Args &a, const uint3
 #ifndef SNP_EMU
 
 #define SNP6_SCAN_WARPS 8
-#define SNP6_SCAN_CTAS 6
+#define SNP6_SCAN_CTAS 5
 #define SNP6_DEC_WARPS 8
-#define SNP6_DEC_CTAS 2
+#define SNP6_DEC_CTAS 3
 
 __global__ void __launch_bounds__(SNP6_SCAN_WARPS * 32, SNP6_SCAN_CTAS) k_tagscan_v6(Scan6Args a) {
     __shared__ uint32_t lut[256];
-    __shared__ uint32_t slots[SNP6_SCAN_WARPS][32 * SNP6_SLOTW];
     lut[threadIdx.x & 255] = tag_lut3_entry(threadIdx.x & 255);
     __syncthreads();
-    tagscan_warp_v6(a, lut, slots[threadIdx.x / SNP_WARP]);
+    tagscan_thread_v6(a, lut);
 }
 
 struct V6DecSmem {
     V6Smem w[SNP6_DEC_WARPS];
-    WarpQueue3 q[SNP6_DEC_WARPS];
     uint32_t lut[256];
 };
+static_assert(sizeof(WarpQueue3) <= sizeof(uint32_t) * 32 * 33, "v3's queue must fit the record area");
 
 __global__ void __launch_bounds__(SNP6_DEC_WARPS * 32, SNP6_DEC_CTAS) k_decode_v6(Decode6Args a) {
     extern __shared__ __align__(16) uint8_t v6_smem_raw[];
     V6DecSmem *s = (V6DecSmem *)v6_smem_raw;
     s->lut[threadIdx.x & 255] = tag_lut3_entry(threadIdx.x & 255);
     __syncthreads();
-    const unsigned w = threadIdx.x / SNP_WARP;
-    decode_warp_v6(a, s->lut, &s->w[w], &s->q[w]);
+    decode_warp_v6(a, s->lut, &s->w[threadIdx.x / SNP_WARP]);
 }
 
 #endif  // !SNP_EMU

@@ -78,8 +78,7 @@ int main(int argc, char **argv) {
     unsigned long long ctr = 0;
     snp::Scan6Args sa{in_base, in_off.data(), in_len.data(), out_cap.data(), out_len.data(), status.data(),
                       0, n, &ctr, ntags.data(), ck.data()};
-    std::vector<uint32_t> slots(32 * SNP6_SLOTW);
-    simt::run_warp([&] { snp::tagscan_warp_v6(sa, lut, slots.data()); });
+    simt::run_warp([&] { snp::tagscan_thread_v6(sa, lut); });
 
     // ---- pass B ----
     ctr = 0;
@@ -89,6 +88,11 @@ int main(int argc, char **argv) {
     memset(sm, 0xCD, sizeof(*sm));
     simt::run_warp([&] { snp::decode_warp_v6(da, lut, sm); });
 
+    if (getenv("SNP6_STATS")) {
+        const snp::V6Stats &t = snp::v6_stats();
+        fprintf(stderr, "v6 stats: tags %lu groups %lu subgroups %lu (fast %lu) rounds %lu trips %lu ctags %lu huge %lu slides %lu flushes %lu\n",
+                t.tags, t.groups, t.subgroups, t.fast, t.rounds, t.trips, t.ctags, t.huge, t.slides, t.flushes);
+    }
     FILE *f = fopen(argv[2], "wb");
     for (uint32_t i = 0; i < n; i++) {
         // guard check: everything between this item's region and its neighbours must be untouched

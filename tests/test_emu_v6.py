@@ -153,6 +153,22 @@ def test_emu_v6_handmade_tag_forms(oracle, emu, tmp_path):
             body += literal(lit[total % 5000: total % 5000 + (off % 7) + 1])
             total += (off % 7) + 1
         items.append(varint(total) + bytes(body))
+    # a literal > 64 bytes at every slot position around the group boundary (head + length never split: pad slot),
+    # with lengths whose low byte looks like a literal head (0x80) or is zero
+    for pre in range(27, 36):
+        for big in (65, 128, 256, 0x180, 1000):
+            body, total = bytearray(), 0
+            for i in range(pre):
+                body += literal(lit[i:i + 1 + (i % 3)])
+                total += 1 + (i % 3)
+            body += literal(lit[100:100 + big])
+            total += big
+            for off, ln in ((1, 20), (big, 33), (5, 4), (total // 2, 64)):
+                body += copy(off, ln)
+                total += ln
+            body += literal(lit[7:7 + big + 3])
+            total += big + 3
+            items.append(varint(total) + bytes(body))
     # long runs of chained far/near copies and literals > 64 interleaved (window slide + re-seed)
     body, total = bytearray(), 0
     for i in range(400):
