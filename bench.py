@@ -130,14 +130,14 @@ def block_checksums(torch, blocks_u8, weights):
     return (v * weights).sum(dim=1)
 
 
-def prepare_batch(torch, engine, n_blocks: int, first_block: int, dev, sub: int = 8192):
+def prepare_batch(torch, engine, n_blocks: int, first_block: int, dev, sub: int = 8192, cap_ratio: float = 0.70):
     """Generate raw blocks, compress them with the GPU compressor, keep dense compressed bytes
     + per-block offsets/lengths + raw checksums.  Raw data is not kept."""
     corpus_dev = {k: torch.from_numpy(v).to(dev) for k, v in load_corpus().items()}
     gw = torch.Generator(device=dev)
     gw.manual_seed(12345)
     weights = torch.randint(-(2**62), 2**62, (BLOCK // 8,), device=dev, generator=gw, dtype=torch.int64) | 1
-    comp_cap = int(n_blocks * BLOCK * 0.70) + (64 << 20)
+    comp_cap = int(n_blocks * BLOCK * cap_ratio) + (64 << 20)
     comp = torch.empty(comp_cap, dtype=torch.uint8, device=dev)
     c_off = torch.empty(n_blocks, dtype=torch.int64, device=dev)
     c_len = torch.empty(n_blocks, dtype=torch.int32, device=dev)

@@ -77,6 +77,7 @@ inline V6Stats &v6_stats() {
 #ifdef SNP_EMU
 __device__ __forceinline__ uint4 ldg_nc_v4(const uint4 *p) { return *p; }
 __device__ __forceinline__ uint4 ldg_v4(const uint4 *p) { return *p; }
+__device__ __forceinline__ uint4 ld_any_v4(const uint4 *p) { return *p; }
 __device__ __forceinline__ void stg_v4(uint4 *p, uint4 v) { *p = v; }
 // stores the low min(m, 4) bytes of r at p
 __device__ __forceinline__ void st_win_bytes4(uint8_t *p, uint32_t r, uint32_t m) {
@@ -87,6 +88,12 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const uint4 *p) { return __ldg(p); }
 __device__ __forceinline__ uint4 ldg_v4(const uint4 *p) {
     uint4 r;
     asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+// generic load (shared or global address), ordered against the surrounding window / output accesses
+__device__ __forceinline__ uint4 ld_any_v4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
     return r;
 }
 __device__ __forceinline__ void stg_v4(uint4 *p, uint4 v) {
@@ -141,45 +148,58 @@ struct Scan6Args {
     uint2 *ck;        // per wave slot: SNP6_CKB checkpoints (ip, op)
 };
 
-// Per-lane 32-byte register window over the lane's own input stream: c holds the 16-byte vector
-// under the cursor, n the next one (loaded when the cursor enters c, i.e. one vector ahead).
-struct InWin6 {
+// Per-lane sequential reader of the lane's own input stream.  A 32-byte shared-memory ring holds the
+// 16-byte vectors vb and vb+1 (vector v in ring[v & 1]); vector vb+2 is already in flight in registers
+// (f), so walking forward never waits for memory, and the tag bytes are read with two LDS at a
+// dynamic word index instead of register selects.
+struct Stream6 {
     const uint4 *base;  // 16-byte aligned; stream byte p sits at byte (skew + p)
     uint32_t last_v;    // last vector index that may be read
-    uint32_t vb;        // vector index held in c (n holds vb + 1)
-    bool valid;
-    uint4 c, n;
-    __device__ __forceinline__ void words(uint32_t wi, uint32_t &w0, uint32_t &w1) {
-        const uint32_t vq = wi >> 2;
-        if (!valid || vq != vb) {
-            if (valid && vq == vb + 1) c = n;
-            else c = ldg_nc_v4(base + min(vq, last_v));
-            n = ldg_nc_v4(base + min(vq + 1, last_v));
+    uint32_t vb;        // ring holds vectors vb, vb + 1
+    uint4 *ring;        // this lane's two vectors in shared memory
+    uint4 f;            // vector vb + 2
+    __device__ __forceinline__ void open(const uint4 *b, uint32_t lv, uint4 *r) {
+        base = b;
+        last_v = lv;
+        ring = r;
+        vb = 0xfffffff0u;
+    }
+    // words holding stream bytes pos .. pos + 7 (pos includes the skew)
+    __device__ __forceinline__ void words(uint32_t pos, uint32_t &w0, uint32_t &w1) {
+        const uint32_t vq = pos >> 4;
+        if (vq != vb) {
+            if (vq == vb + 1) {
+                ring[(vq + 1) & 1] = f;
+            } else {  // first use, or a literal skipped ahead
+                ring[vq & 1] = ldg_nc_v4(base + min(vq, last_v));
+                ring[(vq + 1) & 1] = ldg_nc_v4(base + min(vq + 1, last_v));
+            }
+            f = ldg_nc_v4(base + min(vq + 2, last_v));
             vb = vq;
-            valid = true;
         }
-        const unsigned sel = wi & 3;
-        w0 = sel == 0 ? c.x : sel == 1 ? c.y : sel == 2 ? c.z : c.w;
-        w1 = sel == 0 ? c.y : sel == 1 ? c.z : sel == 2 ? c.w : n.x;
+        const volatile uint32_t *rw = (const volatile uint32_t *)ring;
+        const uint32_t wi = pos >> 2;
+        w0 = rw[wi & 7];
+        w1 = rw[(wi + 1) & 7];
     }
 };
 
-// The persistent scan: every THREAD owns one block at a time, walks its tag chain and fetches the
-// next block when it is done (a flat state machine, so lanes of a warp never wait for each other's
-// blocks).  No shared memory, no collectives: the stream reaches the lane through InWin6.
-__device__ __forceinline__ void tagscan_thread_v6(const Scan6Args &a, const uint32_t *lut) {
-    bool have = false;
+// The persistent scan: every THREAD owns one block at a time and walks its tag chain.  The inner
+// loop is one tag per lane per trip; it is left only when some lane finishes its block, so that the
+// lanes of a warp fetch new blocks without waiting for each other's (long) blocks.
+__device__ __forceinline__ void tagscan_warp_v6(const Scan6Args &a, const uint32_t *lut, uint4 *ring) {
+    bool have = false, exhausted = false;
     size_t slot_idx = 0, item = 0;
     uint32_t ski = 0, n_in = 0, U = 0, ip = 0, op = 0, nslot = 0;
-    InWin6 w;
-    w.base = nullptr;
-    w.last_v = 0;
-    w.vb = 0;
-    w.valid = false;
+    Stream6 s;
+    s.open(nullptr, 0, ring);
     for (;;) {
-        if (!have) {
+        while (!have && !exhausted) {
             const unsigned long long it = atomicAdd(a.next_item, 1ull);
-            if (it >= a.n_items) return;
+            if (it >= a.n_items) {
+                exhausted = true;
+                break;
+            }
             slot_idx = (size_t)it;
             item = a.first_item + slot_idx;
             const uint8_t *in = a.in_base + a.in_off[item];
@@ -200,61 +220,65 @@ __device__ __forceinline__ void tagscan_thread_v6(const Scan6Args &a, const uint
                 continue;
             }
             ski = (uint32_t)((uintptr_t)in & 15);
-            w.base = (const uint4 *)((uintptr_t)in - ski);
-            w.last_v = (ski + n_in - 1) >> 4;
-            w.valid = false;
+            s.open((const uint4 *)((uintptr_t)in - ski), (ski + n_in - 1) >> 4, ring);
             ip = used;
             op = 0;
             nslot = 0;
             have = true;
         }
-        // ---- one tag ----------------------------------------------------------------------------
-        int st = SNP_OK;
-        bool done = false;
-        if (ip >= n_in) {
-            done = true;
-        } else {
-            const uint32_t pos = ski + ip;
-            uint32_t w0, w1;
-            w.words(pos >> 2, w0, w1);
-            const unsigned sh = (pos & 3) * 8;
-            const uint32_t v = __funnelshift_r(w0, w1, sh);
-            const Tag6 t = decode_tag6(v, w1 >> sh, lut[v & 0xff], n_in - ip);
-            if (t.end) {
-                done = true;
-            } else if (!t.is_lit && t.off - 1u >= op) {  // off == 0 || off > produced (:598-601)
-                st = SNP_INVALID_COPY_OFFSET;
-                done = true;
-            } else if (t.take > U - op) {  // :570-573, :603-606
-                st = SNP_DATA_TOO_LONG;
-                done = true;
-            } else {
-                if (t.take) {
-                    const bool huge = t.take > 64u;  // literals only
-                    if (huge && (nslot & (SNP6_T - 1)) == SNP6_T - 1) nslot++;  // pad: head + length stay together
-                    const bool wide = !t.is_lit && t.off >= SNP6_VMAX;          // a 32-bit copy offset
-                    const uint32_t g = nslot / SNP6_T;
-                    if (wide || g >= SNP6_CKB) {
-                        // outside the record format / denser than the checkpoint budget: v3 engine in pass B
-                        a.ntags[slot_idx] = SNP6_NT_FALLBACK;
-                        have = false;
-                        continue;
+        if (__all_sync(SNP_FULL, !have)) break;
+        bool fin = false;
+        do {
+            if (have) {
+                int st = SNP_OK;
+                bool done = false, fb = false;
+                if (ip >= n_in) {
+                    done = true;
+                } else {
+                    const uint32_t pos = ski + ip;
+                    uint32_t w0, w1;
+                    s.words(pos, w0, w1);
+                    const unsigned sh = (pos & 3) * 8;
+                    const uint32_t v = __funnelshift_r(w0, w1, sh);
+                    const Tag6 t = decode_tag6(v, w1 >> sh, lut[v & 0xff], n_in - ip);
+                    if (t.end) {
+                        done = true;
+                    } else if (!t.is_lit && t.off - 1u >= op) {  // off == 0 || off > produced (:598-601)
+                        st = SNP_INVALID_COPY_OFFSET;
+                        done = true;
+                    } else if (t.take > U - op) {  // :570-573, :603-606
+                        st = SNP_DATA_TOO_LONG;
+                        done = true;
+                    } else {
+                        if (t.take) {
+                            const bool huge = t.take > 64u;  // literals only
+                            if (huge && (nslot & (SNP6_T - 1)) == SNP6_T - 1) nslot++;  // pad: head + length stay together
+                            const uint32_t g = nslot / SNP6_T;
+                            // outside the record format (32-bit copy offset) / denser than the checkpoint
+                            // budget: the v3 engine decodes this block in pass B
+                            fb = (!t.is_lit && t.off >= SNP6_VMAX) || g >= SNP6_CKB;
+                            if (!fb && (nslot & (SNP6_T - 1)) == 0) a.ck[slot_idx * SNP6_CKB + g] = make_uint2(ip, op);
+                            nslot += huge ? 2u : 1u;
+                        }
+                        op += t.take;
+                        ip += t.hdr + (t.is_lit ? t.take : 0u);
+                        done = t.partial;
                     }
-                    if ((nslot & (SNP6_T - 1)) == 0) a.ck[slot_idx * SNP6_CKB + g] = make_uint2(ip, op);
-                    nslot += huge ? 2u : 1u;
                 }
-                op += t.take;
-                ip += t.hdr + (t.is_lit ? t.take : 0u);
-                done = t.partial;
+                if (fb) {
+                    a.ntags[slot_idx] = SNP6_NT_FALLBACK;
+                    have = false;
+                    fin = true;
+                } else if (done) {  // the stream ended or failed: this is the block's result
+                    if (st == SNP_OK && op < U) st = SNP_INCOMPLETE;  // Snappy.cs:178-181
+                    a.out_len[item] = st == SNP_OK ? op : 0u;
+                    a.status[item] = st;
+                    a.ntags[slot_idx] = st == SNP_OK ? nslot : 0u;
+                    have = false;
+                    fin = true;
+                }
             }
-        }
-        if (done) {  // the stream ended or failed: this is the block's result
-            if (st == SNP_OK && op < U) st = SNP_INCOMPLETE;  // Snappy.cs:178-181
-            a.out_len[item] = st == SNP_OK ? op : 0u;
-            a.status[item] = st;
-            a.ntags[slot_idx] = st == SNP_OK ? nslot : 0u;
-            have = false;
-        }
+        } while (!__any_sync(SNP_FULL, fin));
     }
 }
 
@@ -352,23 +376,16 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                 sm->gop[lane] = op;
             }
             uint32_t *myrec = sm->rec + lane * 33;
-            uint4 *ring = sm->pslot + lane * 3;  // two 16-byte vectors: vector v lives in ring[v & 1]
-            uint32_t vhave = 0xfffffff0u;        // highest vector index loaded so far
+            Stream6 st6;
+            st6.open(in_v, in_last_v, sm->pslot + lane * 3);
             const uint32_t kmax = min(SNP6_T, nt - SNP6_T * g0);  // the first group of the step is the fullest
             uint32_t k = 0;
 #pragma unroll 1
             for (uint32_t iter = 0; iter < kmax; iter++) {
                 if (k < cnt) {
                     const uint32_t pos = ski + ip;
-                    const uint32_t v0 = pos >> 4, v1 = (pos + 4) >> 4;  // vectors holding bytes pos .. pos+4
-                    if (v1 != vhave) {  // (re)fill: vector v lives in ring[v & 1]
-                        if (v0 != v1 && v0 != vhave) ring[v0 & 1] = ldg_nc_v4(in_v + min(v0, in_last_v));
-                        ring[v1 & 1] = ldg_nc_v4(in_v + min(v1, in_last_v));
-                        vhave = v1;
-                    }
-                    const volatile uint32_t *rw = (const volatile uint32_t *)ring;
-                    const uint32_t wi = pos >> 2;
-                    const uint32_t w0 = rw[wi & 7], w1 = rw[(wi + 1) & 7];
+                    uint32_t w0, w1;
+                    st6.words(pos, w0, w1);
                     const unsigned sh = (pos & 3) * 8;
                     const uint32_t v = __funnelshift_r(w0, w1, sh);
                     const Tag6 t = decode_tag6(v, w1 >> sh, lut[v & 0xff], n_in - ip);
@@ -380,7 +397,6 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                         myrec[k] = (huge ? 0u : t.take) | (t.is_lit ? (SNP6_RLIT | ((ip + t.hdr) << 8)) : (t.off << 8));
                         if (huge) myrec[k + 1] = t.take << 8;  // low byte 0: neither a tag nor a head
                         k += huge ? 2u : 1u;
-                        op += t.take;
                         ip += t.hdr + (t.is_lit ? t.take : 0u);
                     }
                 }
@@ -448,42 +464,58 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                     const bool mine = valid && lane >= t0 && lane < t1 && len != 0;
                     const uint32_t s_pos = d - val;  // copies: P of the first source byte
                     const uint32_t s_end = s_pos + len;
-                    const bool ctype = mine && !is_lit && val < 16u && len > val;  // pattern replication
-                    const bool dep = mine && !is_lit && s_end > ss;                // source produced inside this sub-group
+                    const bool dep = mine && !is_lit && s_end > ss;  // source produced inside this sub-group
                     unsigned pending = __ballot_sync(SNP_FULL, mine);
                     const bool fast = __ballot_sync(SNP_FULL, dep) == 0;  // no in-group dependency: one round, no frontier
                     SNP6_STAT(fast, fast ? 1 : 0);
+                    // Runs: consecutive copies with one offset are the pieces of ONE long match
+                    // (EmitCopy splits at 64 bytes), so a piece whose source reaches into the run's own
+                    // output reads the PERIODIC extension of the `val` bytes in front of the run -- it
+                    // depends on the output before the run only, not on the previous piece.
+                    uint32_t rd = d, pbase = 0, pend = 0xffffffffu, ph = 0;
+                    bool periodic = false;
+                    if (!fast) {
+                        const uint32_t key = (mine && !is_lit) ? val : 0xffffffffu;
+                        const uint32_t pk = __shfl_up_sync(SNP_FULL, key, 1);
+                        const bool cont = mine && !is_lit && lane > t0 && pk == val;
+                        const unsigned heads = __ballot_sync(SNP_FULL, !cont);
+                        const unsigned hl = 31 - __clz(heads & (lanemask_lt() | (1u << lane)));
+                        rd = __shfl_sync(SNP_FULL, d, hl);
+                        periodic = mine && !is_lit && s_end > rd;
+                        if (periodic) {
+                            pbase = rd - val;
+                            pend = rd;
+                            ph = (d - rd) % val;
+                        }
+                    }
+                    const bool ctype = periodic && val < 16u;  // short period: the warp replicates the pattern
                     while (pending) {
                         SNP6_STAT(rounds, 1);
                         bool ready = mine;
                         if (!fast) {
                             const unsigned f = __ffs(pending) - 1;
                             const uint32_t F = __shfl_sync(SNP_FULL, d, f);  // every byte below F is final
-                            ready = mine && ((pending >> lane) & 1u) && (is_lit || s_end <= F || lane == f);
+                            ready = mine && ((pending >> lane) & 1u) && (is_lit || (periodic ? rd : s_end) <= F);
                         }
-                        // ---- (S) one tag per lane, 16 bytes per trip --------------------------------
+                        // ---- (S) one tag per lane, <= 16 bytes per trip -----------------------------
                         {
                             uint32_t rem = (ready && !ctype) ? len : 0u;
                             uint32_t cd = d - wbase;  // window offset of the next byte to write
-                            uint32_t cs = is_lit ? ski + val : s_pos;
+                            uint32_t cs = is_lit ? ski + val : periodic ? pbase + ph : s_pos;
                             while (__any_sync(SNP_FULL, rem != 0)) {
                                 SNP6_STAT(trips, 1);
-                                const uint32_t m = min(rem, 16u);
+                                const uint32_t m = min(min(rem, 16u), pend - cs);
                                 uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
                                 if (m) {
                                     const unsigned sh = cs & 15u;
-                                    uint4 A, B = make_uint4(0, 0, 0, 0);
-                                    if (!is_lit && cs >= hstart) {  // recent output: shared-memory window
-                                        const uint32_t vi = (cs - wbase) >> 4;
-                                        A = win_v[vi];
-                                        B = win_v[vi + 1];
-                                    } else if (is_lit) {  // input stream
-                                        A = ldg_nc_v4(in_v + (cs >> 4));
-                                        if (sh + m > 16u) B = ldg_nc_v4(in_v + (cs >> 4) + 1);
-                                    } else {  // output older than the window: flushed long ago
-                                        A = ldg_v4((const uint4 *)outA + (cs >> 4));
-                                        if (sh + m > 16u) B = ldg_v4((const uint4 *)outA + (cs >> 4) + 1);
-                                    }
+                                    // one generic pointer for the three sources: recent output lives in the
+                                    // shared-memory window, older output and the input stream in global memory
+                                    const uint4 *sp = is_lit ? in_v + (cs >> 4)
+                                                     : cs >= hstart ? win_v + ((cs - wbase) >> 4)
+                                                                    : (const uint4 *)outA + (cs >> 4);
+                                    const uint4 A = ld_any_v4(sp);
+                                    uint4 B = make_uint4(0, 0, 0, 0);
+                                    if (sh + m > 16u) B = ld_any_v4(sp + 1);
                                     funnel16(A, B, sh, r0, r1, r2, r3);
                                 }
                                 const uint32_t mx = __reduce_max_sync(SNP_FULL, m);
@@ -492,13 +524,14 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                                 if (mx > 4) st_win_bytes4(wp + 4, r1, m > 4 ? m - 4 : 0u);
                                 if (mx > 8) st_win_bytes4(wp + 8, r2, m > 8 ? m - 8 : 0u);
                                 if (mx > 12) st_win_bytes4(wp + 12, r3, m > 12 ? m - 12 : 0u);
-                                cs += 16;
-                                cd += 16;
+                                cs += m;
+                                cd += m;
                                 rem -= m;
+                                if (cs == pend) cs = pbase;  // periodic sources wrap at the end of the period
                             }
                         }
-                        // ---- (C) overlapping copies with offset < 16: the warp replicates the pattern
-                        unsigned cm = __ballot_sync(SNP_FULL, ready && ctype);
+                        // ---- (C) periods < 16 (CopyHelpers.IncrementalCopy's pattern replication)
+                        unsigned cm = fast ? 0u : __ballot_sync(SNP_FULL, ready && ctype);
                         while (cm) {
                             SNP6_STAT(ctags, 1);
                             const unsigned i = __ffs(cm) - 1;
@@ -506,9 +539,10 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                             const uint32_t dd = __shfl_sync(SNP_FULL, d, i);
                             const uint32_t ll = __shfl_sync(SNP_FULL, len, i);
                             const uint32_t oo = __shfl_sync(SNP_FULL, val, i);
-                            const uint32_t sp = dd - oo;  // pattern = P in [sp, dd), final since dd == F
+                            const uint32_t sp = __shfl_sync(SNP_FULL, pbase, i);  // pattern = P in [sp, sp + oo), final
+                            const uint32_t p0 = __shfl_sync(SNP_FULL, ph, i);
                             const uint8_t *pat = sp >= hstart ? sm->win + (sp - wbase) : outA + sp;
-                            for (uint32_t k = lane; k < ll; k += SNP_WARP) sm->win[dd - wbase + k] = pat[k % oo];
+                            for (uint32_t k = lane; k < ll; k += SNP_WARP) sm->win[dd - wbase + k] = pat[(p0 + k) % oo];
                         }
                         __syncwarp();  // this round's window bytes are visible to the next round / the flush
                         pending &= ~__ballot_sync(SNP_FULL, ready);
@@ -621,9 +655,10 @@ __device__ __forceinline__ void decode_warp_v6(const Decode6Args &a, const uint3
 
 __global__ void __launch_bounds__(SNP6_SCAN_WARPS * 32, SNP6_SCAN_CTAS) k_tagscan_v6(Scan6Args a) {
     __shared__ uint32_t lut[256];
+    __shared__ uint4 rings[SNP6_SCAN_WARPS * 32 * 3];  // 48-byte pitch per thread
     lut[threadIdx.x & 255] = tag_lut3_entry(threadIdx.x & 255);
     __syncthreads();
-    tagscan_thread_v6(a, lut);
+    tagscan_warp_v6(a, lut, rings + threadIdx.x * 3);
 }
 
 struct V6DecSmem {

@@ -78,7 +78,8 @@ int main(int argc, char **argv) {
     unsigned long long ctr = 0;
     snp::Scan6Args sa{in_base, in_off.data(), in_len.data(), out_cap.data(), out_len.data(), status.data(),
                       0, n, &ctr, ntags.data(), ck.data()};
-    simt::run_warp([&] { snp::tagscan_thread_v6(sa, lut); });
+    std::vector<uint4> rings(32 * 3);
+    simt::run_warp([&] { snp::tagscan_warp_v6(sa, lut, rings.data() + simt::lane() * 3); });
 
     // ---- pass B ----
     ctr = 0;

@@ -41,7 +41,7 @@ def prepare(torch, engine, n, dev, force_class):
     if force_class is not None:
         B.make_blocks = lambda t, c, fb, cnt, d: orig(t, c, fb, cnt, d, force_class=force_class)
     try:
-        return B.prepare_batch(torch, engine, n, 0, dev)
+        return B.prepare_batch(torch, engine, n, 0, dev, cap_ratio=1.02 if force_class is not None and force_class >= 90 else 0.70)
     finally:
         B.make_blocks = orig
 
