@@ -370,6 +370,168 @@ def run_compress(args, torch, dist, engine, world, rank, local, dev):
             "gpu_launches": args.steps, "clocks": clk.summary()}))
 
 
+
+def run_frame(args, torch, engine, rank, local, dev):
+    """BASELINE config 4: the SnappyStream framing format end to end (stream id + 64 KiB chunks with masked
+    CRC32C, raw-vs-compressed choice) over a synthetic stream of the config-2 mixture.  Both calls take
+    HOST buffers, so these are e2e numbers (H2D + kernels + D2H inside the timed region).  Extra line."""
+    import ctypes as C
+    from snappier_b200 import _native as N
+    if rank != 0:
+        return
+    n_blocks = int(args.frame_gib * (1 << 30)) // BLOCK
+    corpus_dev = {k: torch.from_numpy(v).to(dev) for k, v in load_corpus().items()}
+    raw = torch.empty(n_blocks * BLOCK, dtype=torch.uint8).pin_memory()
+    for b0 in range(0, n_blocks, 8192):
+        m = min(8192, n_blocks - b0)
+        raw[b0 * BLOCK:(b0 + m) * BLOCK].copy_(make_blocks(torch, corpus_dev, b0, m, dev).view(-1))
+    torch.cuda.synchronize()
+    L = N.lib()
+    cap = int(L.snp_frame_max_compressed_length(raw.numel()))
+    framed = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    back = torch.empty(raw.numel(), dtype=torch.uint8).pin_memory()
+    w = C.c_size_t(0)
+
+    def compress():
+        st = L.snp_frame_compress(raw.data_ptr(), raw.numel(), framed.data_ptr(), cap, C.byref(w), 0)
+        assert st == 0, st
+        return w.value
+
+    def decompress(nbytes):
+        st = L.snp_frame_decompress(framed.data_ptr(), nbytes, back.data_ptr(), back.numel(), C.byref(w))
+        assert st == 0 and w.value == raw.numel(), (st, w.value)
+
+    launches0 = engine.launch_count
+    nbytes = compress()  # warm-up (allocates the staging buffers)
+    decompress(nbytes)
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            nbytes = compress()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            decompress(nbytes)
+        t2 = time.perf_counter()
+    assert torch.equal(back, raw), "framed round trip differs"
+    # parity of the first chunks against the oracle's framing (outside the timed region)
+    from oracle import pyoracle as O
+    k = 8 * BLOCK
+    want = O.frame_compress(raw[:k].numpy().tobytes())
+    assert framed[:len(want)].numpy().tobytes() == want, "framed bytes differ from the oracle"
+    cg = raw.numel() * args.steps / (t1 - t0) / 1e9
+    dg = raw.numel() * args.steps / (t2 - t1) / 1e9
+    print(json.dumps({
+        "metric": "uncompressed GB/s (SnappyStream framing format, host buffers end to end)",
+        "value": round(2 / (1 / cg + 1 / dg), 3), "unit": "GB/s", "n_gpus": 1, "steps": args.steps, "warmup": 1,
+        "ms_per_step": round((t2 - t0) / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"framed stream: {args.frame_gib} GiB of the config-2 mixture in 64 KiB chunks, one whole-stream "
+                               "snp_frame_compress + snp_frame_decompress per step (pinned host buffers)",
+                   "framed_bytes": int(nbytes), "ratio": round(nbytes / raw.numel(), 4), "hash_mode": "crc32c"},
+        "frame_compress_GBps": round(cg, 3), "frame_decompress_GBps": round(dg, 3),
+        "e2e": {"value": round(2 / (1 / cg + 1 / dg), 3), "unit": "GB/s", "h2d_bytes_per_step": int(raw.numel() + nbytes),
+                "d2h_bytes_per_step": int(raw.numel() + nbytes)},
+        "gpu_launches": "n/a (thread-local default context)" if engine.launch_count == launches0 else int(engine.launch_count - launches0),
+        "clocks": clk.summary()}))
+
+
+def run_roundtrip(args, torch, dist, engine, world, rank, local, dev):
+    """BASELINE config 5: mixed-block corpus (config-2 mixture and config-3 blocks 1:1) sharded by contiguous block
+    range across the GPUs, compress then decompress, verified by per-block checksums.  `value` is the born-sharded
+    round trip (no data-path collective); with N > 1 a root-sourced scatter of the raw blocks and a gather(v) of the
+    compressed blocks over NCCL are timed on a sample beside it (link-bound).  Extra line."""
+    n = min(args.blocks, 1 << 17)  # 8 GiB raw per GPU (64 GiB at 8 GPUs)
+    corpus_dev = {k: torch.from_numpy(v).to(dev) for k, v in load_corpus().items()}
+    raw = torch.empty((n, BLOCK), dtype=torch.uint8, device=dev)
+    for b0 in range(0, n, 8192):
+        m = min(8192, n - b0)
+        a = make_blocks(torch, corpus_dev, rank * n + b0, m, dev)
+        c3 = make_blocks_config3(torch, rank * n + b0, m, dev)
+        odd = (torch.arange(m, device=dev) % 2 == 1)
+        a[odd] = c3[odd]
+        raw[b0:b0 + m] = a
+    gw = torch.Generator(device=dev)
+    gw.manual_seed(12345)
+    weights = torch.randint(-(2**62), 2**62, (BLOCK // 8,), device=dev, generator=gw, dtype=torch.int64) | 1
+    sums = block_checksums(torch, raw.view(-1), weights)
+    slots = torch.empty(n * PITCH, dtype=torch.uint8, device=dev)
+    back = torch.empty(n * BLOCK, dtype=torch.uint8, device=dev)
+    idx = torch.arange(n, device=dev, dtype=torch.int64)
+    r_off, s_off = idx * BLOCK, idx * PITCH
+    r_len = torch.full((n,), BLOCK, dtype=torch.int32, device=dev)
+    s_cap = torch.full((n,), PITCH, dtype=torch.int32, device=dev)
+    s_len = torch.zeros(n, dtype=torch.int32, device=dev)
+    o_len = torch.zeros(n, dtype=torch.int32, device=dev)
+    st1 = torch.zeros(n, dtype=torch.int32, device=dev)
+    st2 = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        engine.compress_batch_device(raw.view(-1), r_off, r_len, slots, s_off, s_cap, s_len, st1, 0, stream)
+        engine.decompress_batch_device(slots, s_off, s_len, back, r_off, r_len, o_len, st2, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = engine.launch_count
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    assert int(st1.abs().sum()) == 0 and int(st2.abs().sum()) == 0
+    assert torch.equal(block_checksums(torch, back, weights), sums), "round trip differs from the source"
+    cbytes = float(s_len.to(torch.int64).sum())
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    b = torch.tensor([float(n) * BLOCK, cbytes], dtype=torch.float64, device=dev)
+    link = None
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        # scatter raw blocks from rank 0 / gather compressed blocks back, on a sample of 2^13 blocks per rank
+        from snappier_b200 import sharding as SH
+        ns = min(n, 1 << 13)
+        tot = ns * world
+        if rank == 0:
+            src = raw[:ns].repeat(world, 1).view(-1)
+            soff = torch.arange(tot, device=dev, dtype=torch.int64) * BLOCK
+            slen = torch.full((tot,), BLOCK, dtype=torch.int32, device=dev)
+        else:
+            src = soff = slen = None
+        barrier()
+        t0 = time.perf_counter()
+        SH.scatter_batch(src, soff, slen, 0, dev)
+        barrier()
+        t1 = time.perf_counter()
+        SH.gather_batch(slots, s_off[:ns], s_len[:ns], 0)
+        barrier()
+        t2 = time.perf_counter()
+        link = {"sample_blocks_per_rank": ns, "scatter_raw_GBps": round(tot * BLOCK / (t1 - t0) / 1e9, 1),
+                "gather_compressed_GBps": round(float(s_len[:ns].to(torch.int64).sum()) * world / (t2 - t1) / 1e9, 1)}
+    if rank == 0:
+        ms = float(t[0])
+        u, c = float(b[0]), float(b[1])
+        print(json.dumps({
+            "metric": "uncompressed GB/s (compress + decompress round trip, 64 KiB blocks)", "value": round(u / ms / 1e6, 2),
+            "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"round trip: {n} mixed 64 KiB blocks per GPU (config-2 mixture and config-3 blocks 1:1), "
+                                   "born sharded by contiguous block range, compress then decompress, checksum-verified",
+                       "ratio": round(c / u, 4), "hash_mode": "crc32c", "parallelism": f"block-range shard x{world}"},
+            "nccl_scatter_gather": link, "gpu_launches": int(engine.launch_count - launches0), "clocks": clk.summary()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------ main
 
 def main():
@@ -384,8 +546,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-blocks", type=int, default=1 << 13)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="decompress", choices=["decompress", "compress"],
-                    help="decompress = BASELINE config 2 (the headline); compress = config 3 (extra, not the driver's line)")
+    ap.add_argument("--workload", default="decompress", choices=["decompress", "compress", "frame", "roundtrip"],
+                    help="decompress = BASELINE config 2 (the headline); compress = config 3, frame = config 4, "
+                         "roundtrip = config 5 (extra lines, not the driver's)")
+    ap.add_argument("--frame-gib", type=float, default=4.0, help="frame workload: stream size (config 4 names 16 GiB)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -407,6 +571,10 @@ def main():
     n = args.blocks
     if args.workload == "compress":
         return run_compress(args, torch, dist, engine, world, rank, local, dev)
+    if args.workload == "frame":
+        return run_frame(args, torch, engine, rank, local, dev)
+    if args.workload == "roundtrip":
+        return run_roundtrip(args, torch, dist, engine, world, rank, local, dev)
 
     comp, c_off, c_len, sums, weights, comp_bytes = prepare_batch(torch, engine, n, rank * n, dev)
     out = torch.empty(n * BLOCK, dtype=torch.uint8, device=dev)

@@ -267,7 +267,7 @@ def test_device_mode_large_batch_properties(engine, oracle):
     status2 = torch.full((n,), -99, dtype=torch.int32, device=dev)
     engine.decompress_batch_device(comp, c_off, c_len, out, o_off, o_cap, o_len, status2, stream)
     torch.cuda.synchronize()
-    assert engine.launch_count - before == 3  # compress, then tag scan + decode (v6)
+    assert engine.launch_count - before == 2
     assert int(status.abs().sum()) == 0 and int(status2.abs().sum()) == 0
     assert bool((o_len == 65536).all())
     want_len = np.array([len(oracle.compress(b)[1]) for b in blocks])
@@ -277,6 +277,17 @@ def test_device_mode_large_batch_properties(engine, oracle):
     ch = comp.view(n, pitch)
     for i in (0, 1, 63, 64, 2047, 4095):
         assert ch[i, : cl[i]].cpu().numpy().tobytes() == oracle.compress(blocks[i % len(blocks)])[1]
+    # the two-pass kernel (SNP_DECOMP_KERNEL=6) on the same device-resident batch, in three waves
+    e6 = _engine_with({"SNP_DECOMP_KERNEL": "6", "SNP_V6_WAVE": "1500"})
+    out.zero_()
+    o_len.zero_()
+    status2.fill_(-99)
+    e6.decompress_batch_device(comp, c_off, c_len, out, o_off, o_cap, o_len, status2, stream)
+    torch.cuda.synchronize()
+    assert e6.launch_count == 6  # 3 waves x (tag scan + decode)
+    assert int(status2.abs().sum()) == 0 and bool((o_len == 65536).all())
+    assert torch.equal(out.view(n // len(blocks), -1), src.view(1, -1).expand(n // len(blocks), -1))
+    e6.close()
 
 
 def _engine_with(env: dict):

@@ -81,7 +81,10 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     variants = args.variants.split(",")
-    engines = {v: engine_with({"SNP_DECOMP_KERNEL": v, "SNP_V6_MIN_ITEMS": "1"}) for v in variants}
+    def env_of(v):  # "5" or "5p3" = kernel 5 with SNP_V5_PREFETCH=3
+        k, _, pf = v.partition("p")
+        return {"SNP_DECOMP_KERNEL": k, "SNP_V6_MIN_ITEMS": "1", "SNP_V5_PREFETCH": pf or "0"}
+    engines = {v: engine_with(env_of(v)) for v in variants}
     prep_engine = engines[variants[0]]
     res = {"blocks": args.blocks, "classes": {}, "small_mix": {}}
     for name, fc in CLASSES:
