@@ -124,20 +124,9 @@ __device__ __noinline__ SparseResult sparse_run_v5(const uint8_t *__restrict__ i
 }
 
 // The dense-tag engine of v3, entered at stream position ip0 with op0 bytes already produced.
-// pf: software prefetch of what the drain rounds are about to read (ncu: 23 % of the stall samples sit on the
-// byte load behind a back-reference, whose sector usually comes from HBM because the resident blocks'
-// working set is 8x the L2): bit 0 = back-reference sources into L1, bit 1 = into L2 only, bit 2 = the input
-// stream one window ahead.
-__device__ __forceinline__ void prefetch_l1(const void *p) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p)));
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p)));
-}
-
 __device__ __noinline__ int decompress_dense_v5(const uint8_t *__restrict__ in, uint32_t n_in, uint8_t *out,
                                                 uint32_t U, uint32_t ip0, uint32_t op0, uint32_t *written,
-                                                const uint32_t *lut, WarpQueue3 *q, int pf) {
+                                                const uint32_t *lut, WarpQueue3 *q) {
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
     *written = 0;
@@ -281,13 +270,6 @@ __device__ __noinline__ int decompress_dense_v5(const uint8_t *__restrict__ in, 
             q->dst[slot] = is_lit ? dst : (dst | 0x80000000u);
             q->src[slot] = is_lit ? pos + hdr : off;
         }
-        if (pf) {
-            if (is_tag && !is_lit) {
-                if (pf & 1) prefetch_l1(out + (dst - off));
-                else if (pf & 2) prefetch_l2(out + (dst - off));
-            }
-            if ((pf & 4) && lane == 0) prefetch_l1(in_w + min(wi + 48, last_w));
-        }
         tail += __popc(tags);
         op += __shfl_sync(SNP_FULL, incl, 31);
         if (lane == 0) q->dst[tail & (SNP_QCAP - 1)] = op;  // sentinel
@@ -308,7 +290,7 @@ k_decompress_v5(const uint8_t *__restrict__ in_base, const uint64_t *__restrict_
                 const uint32_t *__restrict__ in_len, uint8_t *out_base,
                 const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
                 uint32_t *__restrict__ out_len, int32_t *__restrict__ status, size_t n_items,
-                unsigned long long *__restrict__ next_item, int pf) {
+                unsigned long long *__restrict__ next_item) {
     __shared__ uint32_t lut[256];
     __shared__ WarpQueue3 queues[8];
     lut[threadIdx.x & 255] = tag_lut3_entry(threadIdx.x & 255);
@@ -340,7 +322,7 @@ k_decompress_v5(const uint8_t *__restrict__ in_base, const uint64_t *__restrict_
                     st = r.op < U ? SNP_INCOMPLETE : SNP_OK;  // Snappy.cs:178-181
                     w = st == SNP_OK ? r.op : 0;
                 } else {
-                    st = decompress_dense_v5(in, n_in, out, U, r.ip, r.op, &w, lut, q, pf);
+                    st = decompress_dense_v5(in, n_in, out, U, r.ip, r.op, &w, lut, q);
                 }
             }
         }

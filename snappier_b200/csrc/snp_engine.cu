@@ -103,7 +103,6 @@ struct snp_ctx {
                             // issue-bound; 6 = checkpointed two-pass, tag-per-lane decode for batches
                             // of >= v6_min_items blocks (smaller ones take 5): 1.65x faster than 5 on long-tag data,
                             // slower on dense-tag data)
-    int v5_prefetch = 0;        // SNP_V5_PREFETCH: bit 0 back-reference sources -> L1, bit 1 -> L2, bit 2 input stream
     int v6_min_items = 256;     // SNP_V6_MIN_ITEMS: below this the per-thread tag scan cannot fill the GPU
     size_t v6_wave = 131072;    // SNP_V6_WAVE: blocks per scan/decode kernel pair (bounds the checkpoint scratch)
     DevBuf d_v6;                // checkpoint scratch of device-mode / single-call launches
@@ -251,7 +250,7 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
                                                                     out_cap, out_len, status, n, ctr);
         else if (kernel == 5)
             snp::k_decompress_v5<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
-                                                                    out_cap, out_len, status, n, ctr, c->v5_prefetch);
+                                                                    out_cap, out_len, status, n, ctr);
         else
             snp::k_decompress_v4<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
                                                                     out_cap, out_len, status, n, ctr);
@@ -634,7 +633,6 @@ int snp_create(int device, snp_ctx **out) {
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 5);
-    c->v5_prefetch = env_int("SNP_V5_PREFETCH", 0);
     c->v6_min_items = std::max(1, env_int("SNP_V6_MIN_ITEMS", 256));
     c->v6_wave = (size_t)std::max(1, env_int("SNP_V6_WAVE", 131072));
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
