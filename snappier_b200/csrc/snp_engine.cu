@@ -102,7 +102,7 @@ struct snp_ctx {
                             // default; 4 = 3 + TMA-staged input, measured 10 % slower than 3 because the kernel is
                             // issue-bound; 6 = checkpointed two-pass, tag-per-lane decode for batches
                             // of >= v6_min_items blocks (smaller ones take 5): 1.65x faster than 5 on long-tag data,
-                            // slower on dense-tag data, DESIGN.md 4.6)
+                            // slower on dense-tag data, DESIGN.md 4.5)
     int v6_min_items = 256;     // SNP_V6_MIN_ITEMS: below this the per-thread tag scan cannot fill the GPU
     size_t v6_wave = 131072;    // SNP_V6_WAVE: blocks per scan/decode kernel pair (bounds the checkpoint scratch)
     DevBuf d_v6;                // checkpoint scratch of device-mode / single-call launches
