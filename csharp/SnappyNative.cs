@@ -9,6 +9,7 @@
 //   Snappy.DecompressToMemory Snappy.cs:225-234 -> rent GetUncompressedLength bytes, TryDecompress
 //   SnappyStreamCompressor.CompressBlock  Internal/SnappyStreamCompressor.cs:206 -> TryCompress
 using System;
+using System.Buffers;
 using System.IO;
 using System.Runtime.InteropServices;
 
@@ -32,6 +33,8 @@ namespace Snappier.Internal
         [LibraryImport(Lib)] private static partial int snp_uncompressed_length(byte* input, nuint n, uint* len);
         [LibraryImport(Lib)] private static partial int snp_compress(byte* input, nuint n, byte* output, nuint cap, nuint* written, uint hashMode);
         [LibraryImport(Lib)] private static partial int snp_decompress(byte* input, nuint n, byte* output, nuint cap, nuint* written);
+        [LibraryImport(Lib)] private static partial int snp_compress_sequence(byte** segPtr, nuint* segLen, nuint nSeg, byte* output, nuint cap, nuint* written, uint hashMode);
+        [LibraryImport(Lib)] private static partial int snp_decompress_sequence(byte** segPtr, nuint* segLen, nuint nSeg, byte* output, nuint cap, nuint* written);
         [LibraryImport(Lib)] private static partial int snp_create(int device, IntPtr* ctx);
         [LibraryImport(Lib)] private static partial void snp_destroy(IntPtr ctx);
         [LibraryImport(Lib)] private static partial int snp_compress_batch(IntPtr ctx, byte* inBase, ulong* inOff, uint* inLen,
@@ -70,6 +73,45 @@ namespace Snappier.Internal
                 if (st == Status.OutputTooSmall) return false;
                 ThrowFor(st, decompress: false);
                 return true;
+            }
+        }
+
+        // Body of Snappy.Compress(ReadOnlySequence<byte>, IBufferWriter<byte>) (Snappy.cs:82-89).  The native call cuts the
+        // fragments along the segments exactly like SnappyCompressor.Compress(ReadOnlySequence<byte>, ..) (:103-143).
+        internal static void Compress(ReadOnlySequence<byte> input, IBufferWriter<byte> output)
+        {
+            ArgumentNullException.ThrowIfNull(output);
+            if (input.Length > uint.MaxValue)
+                ThrowHelper.ThrowArgumentException($"{nameof(input)} is larger than the maximum size of {uint.MaxValue} bytes.", nameof(input));
+            int nSeg = 0;
+            foreach (ReadOnlyMemory<byte> _ in input) nSeg++;
+            var handles = new MemoryHandle[nSeg];
+            byte** ptr = stackalloc byte*[Math.Max(nSeg, 1)];
+            nuint* len = stackalloc nuint[Math.Max(nSeg, 1)];
+            try
+            {
+                int i = 0;
+                foreach (ReadOnlyMemory<byte> seg in input)
+                {
+                    handles[i] = seg.Pin();
+                    ptr[i] = (byte*)handles[i].Pointer;
+                    len[i] = (nuint)seg.Length;
+                    i++;
+                }
+                // worst case: every fragment carries its own 32 + n/6 + 1 bytes of slack (Helpers.cs:17-46)
+                int cap = checked((int)(input.Length + input.Length / 6 + 64 * (nSeg + input.Length / 32768 + 2)));
+                Span<byte> span = output.GetSpan(cap);
+                fixed (byte* pout = span)
+                {
+                    nuint written;
+                    var st = (Status)snp_compress_sequence(ptr, len, (nuint)nSeg, pout, (nuint)span.Length, &written, (uint)PlatformHashMode);
+                    ThrowFor(st, decompress: false);
+                    output.Advance((int)written);
+                }
+            }
+            finally
+            {
+                foreach (MemoryHandle h in handles) h.Dispose();
             }
         }
 

@@ -106,11 +106,26 @@ uint64_t snp_ctx_launch_count(const snp_ctx *ctx);
 int snp_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written,
                  uint32_t hash_mode);
 
+/* Replaces SnappyCompressor.Compress(ReadOnlySequence<byte>, IBufferWriter<byte>) (SnappyCompressor.cs:85-144)
+ * as called by Snappy.Compress(ReadOnlySequence<byte>, IBufferWriter<byte>) (Snappy.cs:82-89): the input is a
+ * list of host segments.  The reference cuts fragments along the segmentation -- the next fragment is the
+ * first segment's part of the next <= 64 KiB when that part is the whole fragment or >= 32 KiB, otherwise
+ * the whole fragment (SnappyCompressor.cs:103-143) -- so the same bytes in different segments compress to
+ * different bytes; this call reproduces that partition.  One contiguous segment == snp_compress. */
+int snp_compress_sequence(const uint8_t *const *seg_ptr, const size_t *seg_len, size_t n_seg, uint8_t *out,
+                          size_t cap, size_t *written, uint32_t hash_mode);
+
 /* Replaces the one-shot use of SnappyDecompressor in Snappy.TryDecompress
  * (Snappy.cs:172-186): Decompress -> AllDataDecompressed -> Read -> EndOfFile.
  * Data errors take precedence over SNP_OUTPUT_TOO_SMALL, and on TOO_SMALL the
  * first `cap` bytes are still written (SnappyDecompressor.Read, :613-629). */
 int snp_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written);
+
+/* Snappy.Decompress(ReadOnlySequence<byte>, IBufferWriter<byte>) / DecompressToMemory(ReadOnlySequence<byte>)
+ * (Snappy.cs:194-212,246-261): the segments are one block split at arbitrary points; same result and statuses
+ * as snp_decompress on their concatenation. */
+int snp_decompress_sequence(const uint8_t *const *seg_ptr, const size_t *seg_len, size_t n_seg, uint8_t *out,
+                            size_t cap, size_t *written);
 
 /* ---- batched API: the throughput path (an extension; the reference has no
  *      batch call -- each item is one independent Snappy.Compress/Decompress) --

@@ -82,6 +82,24 @@ public:
         return n;
     }
 
+    // Snappy.cs:82-89: Compress(ReadOnlySequence<byte>, IBufferWriter<byte>).  The sequence is its list of segments,
+    // the writer a byte vector that is appended to.  Fragment boundaries follow the segments exactly like
+    // SnappyCompressor.cs:103-143, so the bytes depend on the segmentation.
+    static void Compress(const std::vector<ReadOnlySpan> &input, std::vector<uint8_t> &output) {
+        std::vector<const uint8_t *> ptr;
+        std::vector<size_t> len;
+        size_t total = 0;
+        for (const ReadOnlySpan &s : input) ptr.push_back(s.data), len.push_back(s.size), total += s.size;
+        if (total > 0xffffffffull) throw ArgumentException("input is larger than the maximum size of 4294967295 bytes.");
+        const size_t at = output.size();
+        const size_t cap = total + total / 6 + 64 * (input.size() + total / 32768 + 2);
+        output.resize(at + cap);
+        size_t w = 0;
+        int st = snp_compress_sequence(ptr.data(), len.data(), ptr.size(), output.data() + at, cap, &w, HashMode());
+        output.resize(at + (st == SNP_OK ? w : 0));
+        Throw(st, /*decompress=*/false);
+    }
+
     // Snappy.cs:99-113
     static MemoryOwner CompressToMemory(ReadOnlySpan input) {
         std::vector<uint8_t> buf((size_t)GetMaxCompressedLength((int)input.size));
@@ -130,6 +148,27 @@ public:
         int n = 0;
         TryDecompress(input, {buf.data(), len}, n);
         return MemoryOwner(std::move(buf), (size_t)n);
+    }
+
+    // Snappy.cs:194-212 / 246-261: Decompress(ReadOnlySequence<byte>, IBufferWriter<byte>) and
+    // DecompressToMemory(ReadOnlySequence<byte>): one block split into segments, appended to the writer.
+    static void Decompress(const std::vector<ReadOnlySpan> &input, std::vector<uint8_t> &output) {
+        std::vector<const uint8_t *> ptr;
+        std::vector<size_t> len;
+        uint8_t head[5];
+        size_t nh = 0;
+        for (const ReadOnlySpan &s : input) {
+            ptr.push_back(s.data), len.push_back(s.size);
+            for (size_t i = 0; i < s.size && nh < 5; i++) head[nh++] = s.data[i];
+        }
+        uint32_t U = 0;
+        snp_uncompressed_length(head, nh, &U);  // errors surface from the decode below
+        const size_t at = output.size();
+        output.resize(at + (U ? U : 1));
+        size_t w = 0;
+        int st = snp_decompress_sequence(ptr.data(), len.data(), ptr.size(), output.data() + at, U, &w);
+        output.resize(at + (st == SNP_OK ? w : 0));
+        Throw(st, /*decompress=*/true);
     }
 
     // Snappy.cs:273-282

@@ -25,7 +25,7 @@ SYMBOLS = [
     "snp_abi_version", "snp_status_string", "snp_last_error",
     "snp_max_compressed_length", "snp_get_max_compressed_length", "snp_uncompressed_length",
     "snp_create", "snp_destroy", "snp_ctx_device", "snp_ctx_launch_count",
-    "snp_compress", "snp_decompress",
+    "snp_compress", "snp_decompress", "snp_compress_sequence", "snp_decompress_sequence",
     "snp_compress_batch", "snp_decompress_batch", "snp_uncompressed_length_batch",
     "snp_frame_max_compressed_length", "snp_frame_compress", "snp_frame_uncompressed_length",
     "snp_frame_decompress", "snp_crc32c_batch",
@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
     L.snp_ctx_launch_count.restype = C.c_uint64
     L.snp_compress.argtypes = [vp, sz, vp, sz, C.POINTER(sz), u32]
     L.snp_decompress.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
+    L.snp_compress_sequence.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), u32]
+    L.snp_decompress_sequence.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz)]
     L.snp_compress_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, u32, C.c_int, vp]
     L.snp_decompress_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, C.c_int, vp]
     L.snp_uncompressed_length_batch.argtypes = [vp, vp, vp, vp, vp, vp, sz, C.c_int, vp]

@@ -563,6 +563,88 @@ int host_varint_read(const uint8_t *in, size_t n, uint32_t *v, int *used) {
     return SNP_INCOMPLETE;
 }
 
+// varint(n) ++ concat(CompressFragment(fragment_i)): the body of SnappyCompressor.TryCompress (SnappyCompressor.cs:24-83)
+// for an explicit fragment partition.  The input is given as host segments (copied back to back into device memory);
+// frag_len partitions their concatenation.  Caller holds c->mu.
+int compress_fragments_locked(snp_ctx *c, const uint8_t *const *seg_ptr, const size_t *seg_len, size_t n_seg, size_t n,
+                              const std::vector<uint32_t> &frag_len, uint8_t *out, size_t cap, size_t *written,
+                              uint32_t hash_mode) {
+    cudaStream_t s = c->stream;
+    int rc;
+    const size_t nfrag = frag_len.size();
+    const size_t pitch = (size_t)snp_max_compressed_length(SNP_BLOCK_SIZE) + 5;  // 76496, 16-byte multiple
+    // Snappy's varint header, encoded on the host (VarIntEncoding.Write.cs:5-79).
+    uint8_t hdr[5];
+    size_t hdr_len = 0;
+    {
+        uint32_t v = (uint32_t)n;
+        while (v >= 0x80) hdr[hdr_len++] = (uint8_t)(v | 0x80), v >>= 7;
+        hdr[hdr_len++] = (uint8_t)v;
+    }
+    if (cap < hdr_len) return SNP_OUTPUT_TOO_SMALL;
+    if (nfrag == 0) {  // empty input: the header alone ("" -> 00)
+        memcpy(out, hdr, hdr_len);
+        *written = hdr_len;
+        return SNP_OK;
+    }
+    MetaLayout ml(nfrag);
+    const size_t scan_bytes = align_up(nfrag * 8, 256) + 256;
+    if ((rc = c->d_in.reserve(n + 16))) return rc;
+    if ((rc = c->d_tmp.reserve(nfrag * pitch))) return rc;
+    if ((rc = c->d_meta.reserve(ml.bytes + scan_bytes))) return rc;
+    uint8_t *dm = (uint8_t *)c->d_meta.p;
+    std::vector<uint64_t> off(nfrag), slot(nfrag);
+    std::vector<uint32_t> capv(nfrag, (uint32_t)pitch);
+    uint64_t run = 0;
+    for (size_t f = 0; f < nfrag; f++) {
+        off[f] = run;
+        slot[f] = f * pitch;
+        run += frag_len[f];
+    }
+    CU(cudaMemcpyAsync(dm + ml.in_off, off.data(), nfrag * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dm + ml.out_off, slot.data(), nfrag * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dm + ml.in_len, frag_len.data(), nfrag * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dm + ml.out_cap, capv.data(), nfrag * 4, cudaMemcpyHostToDevice, s));
+    {
+        size_t o = 0;
+        for (size_t i = 0; i < n_seg; i++) {
+            if (seg_len[i]) CU(cudaMemcpyAsync((uint8_t *)c->d_in.p + o, seg_ptr[i], seg_len[i], cudaMemcpyHostToDevice, s));
+            o += seg_len[i];
+        }
+    }
+    auto *d_len = (uint32_t *)(dm + ml.out_len);
+    auto *d_status = (int32_t *)(dm + ml.status);
+    auto *d_scan = (uint64_t *)(dm + ml.bytes);
+    auto *d_total = (uint64_t *)(dm + ml.bytes + align_up(nfrag * 8, 256));
+    rc = launch_compress(c, s, (const uint8_t *)c->d_in.p, (const uint64_t *)(dm + ml.in_off),
+                         (const uint32_t *)(dm + ml.in_len), (uint8_t *)c->d_tmp.p,
+                         (const uint64_t *)(dm + ml.out_off), (const uint32_t *)(dm + ml.out_cap), d_len, d_status,
+                         nfrag, hash_mode, 1);
+    if (rc) return rc;
+    k_frag_scan<<<1, 1024, 0, s>>>(d_len, d_status, d_scan, d_total, nfrag);
+    c->launches++;
+    uint64_t total_bad[2];
+    CU(cudaMemcpyAsync(total_bad, d_total, 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (total_bad[1]) {
+        g_last_error = "internal: fragment compress reported a non-OK status";
+        return SNP_E_CUDA;
+    }
+    size_t total = hdr_len + (size_t)total_bad[0];
+    if (total > cap) return SNP_OUTPUT_TOO_SMALL;  // SnappyCompressor.cs:63-68 (bytesWritten = 0)
+    if ((rc = c->d_out.reserve(total_bad[0] + 16))) return rc;
+    unsigned grid = (unsigned)(nfrag < 4096 ? nfrag : 4096);
+    k_frag_gather<<<grid, 256, 0, s>>>((const uint8_t *)c->d_tmp.p, pitch, d_len, d_scan, (uint8_t *)c->d_out.p,
+                                       nfrag);
+    c->launches++;
+    CU(cudaGetLastError());
+    memcpy(out, hdr, hdr_len);
+    CU(cudaMemcpyAsync(out + hdr_len, c->d_out.p, total_bad[0], cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *written = total;
+    return SNP_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ C ABI ----
@@ -744,65 +826,79 @@ int snp_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *
 
     // SnappyCompressor.cs:40-80: independent 64 KiB fragments, then concatenation.
     const size_t nfrag = (n + SNP_BLOCK_SIZE - 1) / SNP_BLOCK_SIZE;
-    const size_t pitch = (size_t)snp_max_compressed_length(SNP_BLOCK_SIZE) + 5;  // 76496, 16-byte multiple
-    // Snappy's varint header, encoded on the host (VarIntEncoding.Write.cs:5-79).
-    uint8_t hdr[5];
-    size_t hdr_len = 0;
-    {
-        uint32_t v = (uint32_t)n;
-        while (v >= 0x80) hdr[hdr_len++] = (uint8_t)(v | 0x80), v >>= 7;
-        hdr[hdr_len++] = (uint8_t)v;
-    }
-    if (cap < hdr_len) return SNP_OUTPUT_TOO_SMALL;
-    MetaLayout ml(nfrag);
-    const size_t scan_bytes = align_up(nfrag * 8, 256) + 256;
-    if ((rc = c->d_in.reserve(n + 16))) return rc;
-    if ((rc = c->d_tmp.reserve(nfrag * pitch))) return rc;
-    if ((rc = c->d_meta.reserve(ml.bytes + scan_bytes))) return rc;
-    uint8_t *dm = (uint8_t *)c->d_meta.p;
-    std::vector<uint64_t> off(nfrag), slot(nfrag);
-    std::vector<uint32_t> len(nfrag), capv(nfrag, (uint32_t)pitch);
+    std::vector<uint32_t> len(nfrag);
     for (size_t f = 0; f < nfrag; f++) {
-        off[f] = f * (uint64_t)SNP_BLOCK_SIZE;
-        slot[f] = f * pitch;
-        len[f] = (uint32_t)(n - off[f] < SNP_BLOCK_SIZE ? n - off[f] : SNP_BLOCK_SIZE);
+        const size_t o = f * (size_t)SNP_BLOCK_SIZE;
+        len[f] = (uint32_t)(n - o < SNP_BLOCK_SIZE ? n - o : SNP_BLOCK_SIZE);
     }
-    CU(cudaMemcpyAsync(dm + ml.in_off, off.data(), nfrag * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(dm + ml.out_off, slot.data(), nfrag * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(dm + ml.in_len, len.data(), nfrag * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(dm + ml.out_cap, capv.data(), nfrag * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, s));
-    auto *d_len = (uint32_t *)(dm + ml.out_len);
-    auto *d_status = (int32_t *)(dm + ml.status);
-    auto *d_scan = (uint64_t *)(dm + ml.bytes);
-    auto *d_total = (uint64_t *)(dm + ml.bytes + align_up(nfrag * 8, 256));
-    rc = launch_compress(c, s, (const uint8_t *)c->d_in.p, (const uint64_t *)(dm + ml.in_off),
-                         (const uint32_t *)(dm + ml.in_len), (uint8_t *)c->d_tmp.p,
-                         (const uint64_t *)(dm + ml.out_off), (const uint32_t *)(dm + ml.out_cap), d_len, d_status,
-                         nfrag, hash_mode, 1);
+    const uint8_t *one_ptr[1] = {in};
+    const size_t one_len[1] = {n};
+    return compress_fragments_locked(c, one_ptr, one_len, 1, n, len, out, cap, written, hash_mode);
+}
+
+int snp_compress_sequence(const uint8_t *const *seg_ptr, const size_t *seg_len, size_t n_seg, uint8_t *out, size_t cap,
+                          size_t *written, uint32_t hash_mode) {
+    if (!written || (n_seg && (!seg_ptr || !seg_len)) || (!out && cap) || hash_mode > SNP_HASH_MUL)
+        return SNP_E_INVALID_ARG;
+    *written = 0;
+    size_t n = 0;
+    for (size_t i = 0; i < n_seg; i++) {
+        if (!seg_ptr[i] && seg_len[i]) return SNP_E_INVALID_ARG;
+        if (overlaps(seg_ptr[i], seg_len[i], out, cap)) return SNP_E_OVERLAP;
+        n += seg_len[i];
+    }
+    if (n > 0xffffffffull) return SNP_E_INVALID_ARG;  // SnappyCompressor.cs:88-91
+    if (cap == 0) return SNP_OUTPUT_TOO_SMALL;
+    // SnappyCompressor.cs:103-143: the next fragment is the first segment's part of the next <= 64 KiB when the
+    // fragment is contiguous or that part is >= 32 KiB, otherwise the whole (copied) fragment -- so the fragment
+    // boundaries, hence the compressed bytes, depend on the segmentation.
+    std::vector<uint32_t> len;
+    {
+        size_t i = 0, o = 0, left = n;
+        while (left) {
+            while (i < n_seg && o == seg_len[i]) i++, o = 0;  // empty segments carry no bytes
+            const size_t frag = left < SNP_BLOCK_SIZE ? left : SNP_BLOCK_SIZE;
+            const size_t first = seg_len[i] - o < frag ? seg_len[i] - o : frag;
+            const size_t take = (first == frag || first >= SNP_BLOCK_SIZE / 2) ? first : frag;
+            len.push_back((uint32_t)take);
+            left -= take;
+            size_t adv = take;
+            while (adv) {
+                const size_t step = seg_len[i] - o < adv ? seg_len[i] - o : adv;
+                o += step;
+                adv -= step;
+                if (o == seg_len[i] && adv) i++, o = 0;
+            }
+        }
+    }
+    snp_ctx *c;
+    int rc = default_ctx(&c);
     if (rc) return rc;
-    k_frag_scan<<<1, 1024, 0, s>>>(d_len, d_status, d_scan, d_total, nfrag);
-    c->launches++;
-    uint64_t total_bad[2];
-    CU(cudaMemcpyAsync(total_bad, d_total, 16, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (total_bad[1]) {
-        g_last_error = "internal: fragment compress reported a non-OK status";
-        return SNP_E_CUDA;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    return compress_fragments_locked(c, seg_ptr, seg_len, n_seg, n, len, out, cap, written, hash_mode);
+}
+
+int snp_decompress_sequence(const uint8_t *const *seg_ptr, const size_t *seg_len, size_t n_seg, uint8_t *out,
+                            size_t cap, size_t *written) {
+    // Snappy.Decompress(ReadOnlySequence<byte>, ..) feeds the segments to one decoder in order (Snappy.cs:194-212,
+    // 246-261): the result is that of decoding their concatenation.  The batch engine needs whole blocks, so the
+    // segments are joined on the host first (the resumable split-input state machine stays out of scope).
+    if (!written || (n_seg && (!seg_ptr || !seg_len)) || (!out && cap)) return SNP_E_INVALID_ARG;
+    *written = 0;
+    size_t n = 0;
+    for (size_t i = 0; i < n_seg; i++) {
+        if (!seg_ptr[i] && seg_len[i]) return SNP_E_INVALID_ARG;
+        n += seg_len[i];
     }
-    size_t total = hdr_len + (size_t)total_bad[0];
-    if (total > cap) return SNP_OUTPUT_TOO_SMALL;  // SnappyCompressor.cs:63-68 (bytesWritten = 0)
-    if ((rc = c->d_out.reserve(total_bad[0] + 16))) return rc;
-    unsigned grid = (unsigned)(nfrag < 4096 ? nfrag : 4096);
-    k_frag_gather<<<grid, 256, 0, s>>>((const uint8_t *)c->d_tmp.p, pitch, d_len, d_scan, (uint8_t *)c->d_out.p,
-                                       nfrag);
-    c->launches++;
-    CU(cudaGetLastError());
-    memcpy(out, hdr, hdr_len);
-    CU(cudaMemcpyAsync(out + hdr_len, c->d_out.p, total_bad[0], cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    *written = total;
-    return SNP_OK;
+    if (n_seg == 1) return snp_decompress(seg_ptr[0], seg_len[0], out, cap, written);
+    std::vector<uint8_t> joined(n);
+    size_t o = 0;
+    for (size_t i = 0; i < n_seg; i++) {
+        if (seg_len[i]) memcpy(joined.data() + o, seg_ptr[i], seg_len[i]);
+        o += seg_len[i];
+    }
+    return snp_decompress(joined.data(), n, out, cap, written);
 }
 
 int snp_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written) {

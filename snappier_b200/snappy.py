@@ -112,6 +112,46 @@ def compress_to_array(input, hash_mode: int | None = None) -> bytes:
     return compress_to_memory(input, hash_mode).tobytes()
 
 
+def _segments(segments):
+    """list of byte-likes -> (kept-alive arrays, void*[n], size_t[n])"""
+    arrs = [_ro(x) for x in segments]
+    ptrs = (C.c_void_p * max(len(arrs), 1))(*[a.ctypes.data if a.size else None for a in arrs])
+    lens = (C.c_size_t * max(len(arrs), 1))(*[a.size for a in arrs])
+    return arrs, ptrs, lens
+
+
+def compress_sequence(segments, hash_mode: int | None = None) -> bytes:
+    """Snappy.Compress(ReadOnlySequence<byte>, IBufferWriter<byte>) (Snappy.cs:82-89) -> the bytes handed to the
+    writer.  `segments` is the sequence's list of memory segments: the reference cuts its fragments along them
+    (SnappyCompressor.cs:103-143), so the output depends on the segmentation, not only on the bytes."""
+    arrs, ptrs, lens = _segments(segments)
+    total = sum(a.size for a in arrs)
+    if total > 0xFFFFFFFF:
+        raise ArgumentException("input is larger than the maximum size of 4294967295 bytes.")
+    # every fragment may be shorter than 64 KiB here, so size for the worst case per segment boundary
+    cap = get_max_compressed_length(total) + 64 * (len(arrs) + total // 32768 + 1)
+    out = np.empty(cap, np.uint8)
+    w = C.c_size_t(0)
+    st = N.lib().snp_compress_sequence(ptrs, lens, len(arrs), _ptr(out), out.size, C.byref(w),
+                                       default_hash_mode if hash_mode is None else hash_mode)
+    _raise_for_status(st, "compress")
+    return out[: w.value].tobytes()
+
+
+def decompress_sequence(segments) -> bytes:
+    """Snappy.DecompressToMemory(ReadOnlySequence<byte>) (Snappy.cs:246-261): one block split into segments."""
+    arrs, ptrs, lens = _segments(segments)
+    head = _ro(b"".join(a[:5].tobytes() for a in arrs)[:5])  # the varint prefix may straddle segments
+    v = C.c_uint32(0)
+    n = v.value if N.lib().snp_uncompressed_length(_ptr(head), head.size, C.byref(v)) == N.OK else 0
+    n = v.value
+    out = np.empty(max(n, 1), np.uint8)
+    w = C.c_size_t(0)
+    st = N.lib().snp_decompress_sequence(ptrs, lens, len(arrs), _ptr(out), n, C.byref(w))
+    _raise_for_status(st, "decompress")
+    return out[: w.value].tobytes()
+
+
 def get_uncompressed_length(input) -> int:
     """Snappy.GetUncompressedLength (Snappy.cs:142-143)."""
     a = _ro(input)

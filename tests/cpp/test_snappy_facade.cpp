@@ -1,6 +1,7 @@
 // C++ test of include/snappier_b200.hpp, written to read like the reference's own
 // block tests (/root/reference/Snappier.Tests/SnappyTests.cs).  Built and run by
 // tests/test_gpu_cpp_facade.py on the GPU box:  ./test_snappy_facade <fixture dir>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -53,6 +54,27 @@ int main(int argc, char **argv) {
         std::vector<uint8_t> bad = Snappy::CompressToArray({(const uint8_t *)"making sure we don't crash with corrupted input", 47});
         bad[1]--; bad[3]++;
         CHECK(throws<InvalidDataException>([&] { Snappy::DecompressToArray(ro(bad)); }));
+    }
+    // SnappyTests.cs:122-174: the ReadOnlySequence / IBufferWriter overloads, input split into 16/32/64 KiB and
+    // ragged segments.  One segment == the span overload; any segmentation round-trips; a split block decodes.
+    for (size_t seg : {size_t(16384), size_t(32768), size_t(65536), size_t(1000), size_t(40000)}) {
+        std::vector<ReadOnlySpan> seq;
+        for (size_t o = 0; o < input.size(); o += seg) seq.push_back({input.data() + o, std::min(seg, input.size() - o)});
+        std::vector<uint8_t> c;
+        Snappy::Compress(seq, c);
+        CHECK(Snappy::DecompressToArray(ro(c)) == input);
+        std::vector<ReadOnlySpan> cseq;
+        for (size_t o = 0; o < c.size(); o += 1024) cseq.push_back({c.data() + o, std::min(size_t(1024), c.size() - o)});
+        std::vector<uint8_t> back;
+        Snappy::Decompress(cseq, back);
+        CHECK(back == input);
+        if (seg == 65536) CHECK(c == expect);  // 64 KiB segments give the span overload's fragments
+    }
+    {
+        std::vector<ReadOnlySpan> one{ro(input)};
+        std::vector<uint8_t> c;
+        Snappy::Compress(one, c);
+        CHECK(c == expect);
     }
     // SnappyTests.cs:178-202 edge strings
     for (std::string s : {std::string(""), std::string("a"), std::string("ab"), std::string("abc"),

@@ -102,6 +102,66 @@ def test_whole_files_single_call_api(oracle, fixtures):
         assert S.decompress_to_array(c) == d
 
 
+def _sequence_fragments(seg_lens):
+    """The fragment partition of SnappyCompressor.Compress(ReadOnlySequence<byte>, ..), restated from
+    SnappyCompressor.cs:103-143: the next fragment is the first segment's part of the next <= 64 KiB when that part is the
+    whole fragment (fragment.IsSingleSegment) or at least 32 KiB, otherwise the whole (copied) fragment."""
+    segs = [n for n in seg_lens if n]
+    frags, i, o, left = [], 0, 0, sum(segs)
+    while left:
+        frag = min(left, 65536)
+        first = min(segs[i] - o, frag)
+        take = first if (first == frag or first >= 32768) else frag
+        frags.append(take)
+        left -= take
+        while take:
+            step = min(segs[i] - o, take)
+            o += step
+            take -= step
+            if o == segs[i]:
+                i, o = i + 1, 0
+    return frags
+
+
+def test_sequence_overloads_follow_the_segmentation(oracle, fixtures):
+    """Snappy.Compress(ReadOnlySequence, IBufferWriter) / DecompressToMemory(ReadOnlySequence) (SnappyTests.cs:122-174 and
+    :333-399 split the input into 16/32/64 KiB and 1024-byte segments): bytes equal varint ++ the oracle's
+    CompressFragment of every fragment of the reference's partition, for regular and ragged segmentations."""
+    from snappier_b200 import snappy as S
+    data = fixtures["corpus/lcet10.txt"] + fixtures["corpus/kppkn.gtb"][:100000]
+    rng = np.random.default_rng(31)
+    plans = [[len(data)], [16384] * 40, [32768] * 20, [65536] * 10, [1024] * 700, [40000, 1000, 70000, 5, 200000],
+             [32767, 32769, 65536, 1, 65535, 131072], [int(x) for x in rng.integers(1, 90000, size=64)]]
+    for plan in plans:
+        segs, o = [], 0
+        for n in plan:
+            if o >= len(data):
+                break
+            segs.append(data[o:o + n])
+            o += n
+        if o < len(data):
+            segs.append(data[o:])
+        want = bytearray(oracle.varint_write(len(data)))
+        o = 0
+        for n in _sequence_fragments([len(x) for x in segs]):
+            buf = np.zeros(oracle.max_compressed_length(n), np.uint8)
+            frag = np.frombuffer(data[o:o + n], np.uint8)
+            w = oracle.lib().orc_compress_fragment(frag.ctypes.data, n, buf.ctypes.data, 0)
+            want += buf[:w].tobytes()
+            o += n
+        got = S.compress_sequence(segs)
+        assert got == bytes(want), plan[:6]
+        assert oracle.decompress(got)[1] == data
+        # the block arrives split at arbitrary points (SnappyTests.cs:357-378: 1024-byte segments)
+        cuts = sorted(set(int(x) for x in rng.integers(0, len(got), size=9)) | {0, 1, 2, len(got)})
+        pieces = [got[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+        assert S.decompress_sequence(pieces) == data
+    assert S.compress_sequence([data]) == S.compress_to_array(data)  # one segment == the span overload
+    assert S.compress_sequence([]) == b"\x00" and S.decompress_sequence([b"\x00"]) == b""
+    with pytest.raises(S.InvalidDataException):
+        S.decompress_sequence([got[:100], got[100:200]])  # truncated block
+
+
 def test_output_sizing_semantics(oracle):
     """SnappyTests.cs:41-118."""
     from snappier_b200 import snappy as S
