@@ -507,14 +507,15 @@ def run_roundtrip(args, torch, dist, engine, world, rank, local, dev):
             slen = torch.full((tot,), BLOCK, dtype=torch.int32, device=dev)
         else:
             src = soff = slen = None
-        barrier()
-        t0 = time.perf_counter()
-        SH.scatter_batch(src, soff, slen, 0, dev)
-        barrier()
-        t1 = time.perf_counter()
-        SH.gather_batch(slots, s_off[:ns], s_len[:ns], 0)
-        barrier()
-        t2 = time.perf_counter()
+        for it in range(2):  # the first pass pays NCCL's lazy peer-to-peer connection setup: time the second
+            barrier()
+            t0 = time.perf_counter()
+            SH.scatter_batch(src, soff, slen, 0, dev)
+            barrier()
+            t1 = time.perf_counter()
+            SH.gather_batch(slots, s_off[:ns], s_len[:ns], 0)
+            barrier()
+            t2 = time.perf_counter()
         link = {"sample_blocks_per_rank": ns, "scatter_raw_GBps": round(tot * BLOCK / (t1 - t0) / 1e9, 1),
                 "gather_compressed_GBps": round(float(s_len[:ns].to(torch.int64).sum()) * world / (t2 - t1) / 1e9, 1)}
     if rank == 0:

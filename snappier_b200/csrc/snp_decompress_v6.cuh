@@ -61,7 +61,7 @@ struct alignas(16) V6Smem {  // pass B, per warp
 
 #ifdef SNP_EMU
 struct V6Stats {
-    unsigned long groups, subgroups, rounds, trips, ctags, huge, slides, tags, flushes, fast;
+    unsigned long groups, subgroups, rounds, trips, ctags, huge, slides, tags, flushes, fast, hops;
 };
 inline V6Stats &v6_stats() {
     static V6Stats s{};
@@ -489,19 +489,56 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                         }
                     }
                     const bool ctype = periodic && val < 16u;  // short period: the warp replicates the pattern
+                    // Source forwarding: a copy whose source lies inside ONE plain tag of this sub-group reads
+                    // that tag's own source instead (the literal's input bytes, or the older output the tag
+                    // copies from), so it does not have to wait for it.  Every hop follows the tag's current
+                    // source, i.e. chains shorten by pointer doubling; what cannot be forwarded (a source that
+                    // straddles tags) waits for the frontier as before.
+                    bool src_in = is_lit;                        // the source is the input stream
+                    uint32_t sp = is_lit ? ski + val : s_pos;    // first source byte (input or P coordinates)
+                    bool single = fast;                          // no waiting needed: one round
+                    if (!fast) {
+                        bool stuck = false;
+#pragma unroll 1
+                        for (int hop = 0; hop < 3; hop++) {
+                            const bool need = mine && !src_in && !periodic && !stuck && sp + len > ss;
+                            if (!__any_sync(SNP_FULL, need)) break;
+                            SNP6_STAT(hops, 1);
+                            uint32_t j = 0;  // last lane whose tag starts at or before sp (d is non-decreasing over lanes)
+#pragma unroll
+                            for (uint32_t step = 16; step; step >>= 1) {
+                                const uint32_t dq = __shfl_sync(SNP_FULL, d, j + step);
+                                if (dq <= sp) j += step;
+                            }
+                            const uint32_t dj = __shfl_sync(SNP_FULL, d, j);
+                            const uint32_t ej = __shfl_sync(SNP_FULL, e, j);
+                            const uint32_t spj = __shfl_sync(SNP_FULL, sp, j);
+                            const unsigned fj = __shfl_sync(SNP_FULL, (mine && !periodic ? 1u : 0u) | (src_in ? 2u : 0u), j);
+                            if (need) {
+                                if (j >= t0 && (fj & 1u) && sp >= dj && sp + len <= ej) {
+                                    src_in = (fj & 2u) != 0;
+                                    sp = spj + (sp - dj);
+                                } else {
+                                    stuck = true;
+                                }
+                            }
+                        }
+                        const bool waits = mine && !src_in && (periodic ? rd > ss : sp + len > ss);
+                        single = __ballot_sync(SNP_FULL, waits) == 0;
+                    }
                     while (pending) {
                         SNP6_STAT(rounds, 1);
                         bool ready = mine;
-                        if (!fast) {
+                        if (!single) {
                             const unsigned f = __ffs(pending) - 1;
                             const uint32_t F = __shfl_sync(SNP_FULL, d, f);  // every byte below F is final
-                            ready = mine && ((pending >> lane) & 1u) && (is_lit || (periodic ? rd : s_end) <= F);
+                            ready = mine && ((pending >> lane) & 1u) && (src_in || (periodic ? rd : sp + len) <= F);
                         }
                         // ---- (S) one tag per lane, <= 16 bytes per trip -----------------------------
                         {
                             uint32_t rem = (ready && !ctype) ? len : 0u;
                             uint32_t cd = d - wbase;  // window offset of the next byte to write
-                            uint32_t cs = is_lit ? ski + val : periodic ? pbase + ph : s_pos;
+                            uint32_t cs = periodic ? pbase + ph : sp;
                             while (__any_sync(SNP_FULL, rem != 0)) {
                                 SNP6_STAT(trips, 1);
                                 const uint32_t m = min(min(rem, 16u), pend - cs);
@@ -510,12 +547,12 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                                     const unsigned sh = cs & 15u;
                                     // one generic pointer for the three sources: recent output lives in the
                                     // shared-memory window, older output and the input stream in global memory
-                                    const uint4 *sp = is_lit ? in_v + (cs >> 4)
+                                    const uint4 *vp = src_in ? in_v + (cs >> 4)
                                                      : cs >= hstart ? win_v + ((cs - wbase) >> 4)
                                                                     : (const uint4 *)outA + (cs >> 4);
-                                    const uint4 A = ld_any_v4(sp);
+                                    const uint4 A = ld_any_v4(vp);
                                     uint4 B = make_uint4(0, 0, 0, 0);
-                                    if (sh + m > 16u) B = ld_any_v4(sp + 1);
+                                    if (sh + m > 16u) B = ld_any_v4(vp + 1);
                                     funnel16(A, B, sh, r0, r1, r2, r3);
                                 }
                                 const uint32_t mx = __reduce_max_sync(SNP_FULL, m);
@@ -539,9 +576,9 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                             const uint32_t dd = __shfl_sync(SNP_FULL, d, i);
                             const uint32_t ll = __shfl_sync(SNP_FULL, len, i);
                             const uint32_t oo = __shfl_sync(SNP_FULL, val, i);
-                            const uint32_t sp = __shfl_sync(SNP_FULL, pbase, i);  // pattern = P in [sp, sp + oo), final
+                            const uint32_t pb = __shfl_sync(SNP_FULL, pbase, i);  // pattern = P in [pb, pb + oo), final
                             const uint32_t p0 = __shfl_sync(SNP_FULL, ph, i);
-                            const uint8_t *pat = sp >= hstart ? sm->win + (sp - wbase) : outA + sp;
+                            const uint8_t *pat = pb >= hstart ? sm->win + (pb - wbase) : outA + pb;
                             for (uint32_t k = lane; k < ll; k += SNP_WARP) sm->win[dd - wbase + k] = pat[(p0 + k) % oo];
                         }
                         __syncwarp();  // this round's window bytes are visible to the next round / the flush

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Compress throughput of engine settings (diagnostics): python tools/compress_bench.py [--blocks 32768]
-Variants are "ctas[:persist_mb]" = SNP_COMP_CTAS_PER_SM and SNP_COMP_L2_PERSIST_MB, e.g. 8,4,2:96,1:96."""
+Variants are "ctas[:persist_mb]" = SNP_COMP_CTAS_PER_SM and SNP_COMP_L2_PERSIST_MB (e.g. 8,4,2:96) or "kN" = SNP_COMP_KERNEL=N."""
 from __future__ import annotations
 
 import argparse
@@ -42,8 +42,13 @@ def main():
     res = {}
     ref_len = {}
     for v in args.variants.split(","):
-        ctas, _, mb = v.partition(":")
-        eng = CB.engine_with({"SNP_COMP_CTAS_PER_SM": ctas, "SNP_COMP_L2_PERSIST_MB": mb or "0"})
+        env = {"SNP_COMP_CTAS_PER_SM": "8", "SNP_COMP_L2_PERSIST_MB": "0", "SNP_COMP_KERNEL": "3"}
+        if v.startswith("k"):  # "k2" = SNP_COMP_KERNEL=2
+            env["SNP_COMP_KERNEL"] = v[1:]
+        else:
+            ctas, _, mb = v.partition(":")
+            env.update({"SNP_COMP_CTAS_PER_SM": ctas, "SNP_COMP_L2_PERSIST_MB": mb or "0"})
+        eng = CB.engine_with(env)
         row = {}
         for name, raw in data.items():
             best = 1e30
