@@ -466,7 +466,8 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                     const uint32_t s_end = s_pos + len;
                     const bool dep = mine && !is_lit && s_end > ss;  // source produced inside this sub-group
                     unsigned pending = __ballot_sync(SNP_FULL, mine);
-                    const bool fast = __ballot_sync(SNP_FULL, dep) == 0;  // no in-group dependency: one round, no frontier
+                    const unsigned depm = __ballot_sync(SNP_FULL, dep);
+                    const bool fast = depm == 0;  // no in-group dependency: one round, no frontier
                     SNP6_STAT(fast, fast ? 1 : 0);
                     // Runs: consecutive copies with one offset are the pieces of ONE long match
                     // (EmitCopy splits at 64 bytes), so a piece whose source reaches into the run's own
@@ -498,7 +499,9 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                     uint32_t sp = is_lit ? ski + val : s_pos;    // first source byte (input or P coordinates)
                     bool single = fast;                          // no waiting needed: one round
                     if (!fast) {
-                        bool stuck = false;
+                        // (a hop costs ~45 instructions: worth it for chains -- records, markup --, not for the one or
+                        //  two dependent tags of a text group, which simply take a second round)
+                        bool stuck = __popc(depm) < 4;
 #pragma unroll 1
                         for (int hop = 0; hop < 3; hop++) {
                             const bool need = mine && !src_in && !periodic && !stuck && sp + len > ss;

@@ -104,7 +104,8 @@ struct snp_ctx {
                             // of >= v6_min_items blocks (smaller ones take 5): 1.65x faster than 5 on long-tag data,
                             // slower on dense-tag data)
     int v6_min_items = 256;     // SNP_V6_MIN_ITEMS: below this the per-thread tag scan cannot fill the GPU
-    size_t v6_wave = 131072;    // SNP_V6_WAVE: blocks per scan/decode kernel pair (bounds the checkpoint scratch)
+    size_t v6_wave = 262144;    // SNP_V6_WAVE: blocks per scan/decode kernel pair (bounds the checkpoint scratch: 6 KB per
+                                // block; the thread-per-block scan needs >= 189 k blocks in flight to fill the GPU)
     DevBuf d_v6;                // checkpoint scratch of device-mode / single-call launches
     cudaEvent_t v6_done = nullptr;  // orders users of d_v6 that arrive on different streams
     cudaStream_t v6_last_stream = nullptr;
@@ -738,7 +739,7 @@ int snp_create(int device, snp_ctx **out) {
     CU(cudaStreamSynchronize(c->stream));
     c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 5);
     c->v6_min_items = std::max(1, env_int("SNP_V6_MIN_ITEMS", 256));
-    c->v6_wave = (size_t)std::max(1, env_int("SNP_V6_WAVE", 131072));
+    c->v6_wave = (size_t)std::max(1, env_int("SNP_V6_WAVE", 262144));
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     {

@@ -75,6 +75,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=1 << 15)
     ap.add_argument("--variants", default="5,6")
     ap.add_argument("--small", default="64,256,1024,4096")
+    ap.add_argument("--classes", default="", help="comma-separated subset of class names (default: all)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "class_bench.json"))
     args = ap.parse_args()
     import torch
@@ -83,11 +84,14 @@ def main():
     variants = args.variants.split(",")
     def env_of(v):  # "5" or "5p3" = kernel 5 with SNP_V5_PREFETCH=3
         k, _, pf = v.partition("p")
-        return {"SNP_DECOMP_KERNEL": k, "SNP_V6_MIN_ITEMS": "1", "SNP_V5_PREFETCH": pf or "0"}
+        return {"SNP_DECOMP_KERNEL": k, "SNP_V6_MIN_ITEMS": "1", "SNP_V6_WAVE": os.environ.get("SNP_V6_WAVE", "262144")}
     engines = {v: engine_with(env_of(v)) for v in variants}
     prep_engine = engines[variants[0]]
     res = {"blocks": args.blocks, "classes": {}, "small_mix": {}}
+    wanted = [c for c in args.classes.split(",") if c]
     for name, fc in CLASSES:
+        if wanted and name not in wanted:
+            continue
         comp, c_off, c_len, sums, weights, cbytes = prepare(torch, prep_engine, args.blocks, dev, fc)
         row = {"ratio": round(cbytes / (args.blocks * B.BLOCK), 4)}
         for v, e in engines.items():
