@@ -672,7 +672,7 @@ def main():
         traffic = int(per_block * n) if per_block else None  # ncu --set full capture, scaled to this launch
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the host-core baseline is reported by the single-GPU run only
         nc = min(args.cpu_blocks, n)
         cb = int(c_off[nc - 1] + c_len[nc - 1])
         threads = os.cpu_count() or 1
