@@ -61,7 +61,7 @@ struct alignas(16) V6Smem {  // pass B, per warp
 
 #ifdef SNP_EMU
 struct V6Stats {
-    unsigned long groups, subgroups, rounds, trips, ctags, huge, slides, tags, flushes, fast, hops;
+    unsigned long groups, subgroups, rounds, trips, ctags, huge, slides, tags, flushes, fast, hops, stuck_kind, stuck_straddle;
 };
 inline V6Stats &v6_stats() {
     static V6Stats s{};
@@ -523,6 +523,10 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                                     sp = spj + (sp - dj);
                                 } else {
                                     stuck = true;
+#ifdef SNP_EMU
+                                    if (!(fj & 1u)) v6_stats().stuck_kind++;
+                                    else v6_stats().stuck_straddle++;
+#endif
                                 }
                             }
                         }

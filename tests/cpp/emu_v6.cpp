@@ -91,8 +91,8 @@ int main(int argc, char **argv) {
 
     if (getenv("SNP6_STATS")) {
         const snp::V6Stats &t = snp::v6_stats();
-        fprintf(stderr, "v6 stats: tags %lu groups %lu subgroups %lu (fast %lu) rounds %lu trips %lu ctags %lu huge %lu slides %lu flushes %lu hops %lu\n",
-                t.tags, t.groups, t.subgroups, t.fast, t.rounds, t.trips, t.ctags, t.huge, t.slides, t.flushes, t.hops);
+        fprintf(stderr, "v6 stats: tags %lu groups %lu subgroups %lu (fast %lu) rounds %lu trips %lu ctags %lu huge %lu slides %lu flushes %lu hops %lu stuck(kind %lu straddle %lu)\n",
+                t.tags, t.groups, t.subgroups, t.fast, t.rounds, t.trips, t.ctags, t.huge, t.slides, t.flushes, t.hops, t.stuck_kind, t.stuck_straddle);
     }
     FILE *f = fopen(argv[2], "wb");
     for (uint32_t i = 0; i < n; i++) {
