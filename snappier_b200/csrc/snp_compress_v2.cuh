@@ -225,7 +225,7 @@ __device__ __forceinline__ uint32_t fp16(uint32_t x) { return (x * 0x9E3779B1u) 
 
 template <int HASH_MODE>
 __device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in, uint32_t n, OutCursor &o,
-                                                  uint32_t *table, const uint16_t *lut, const uint32_t *sched) {
+                                                  uint32_t *table, const uint16_t *lut, const uint32_t *sched, uint32_t w0) {
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
     const int tsize = table_size_for(n);
@@ -242,6 +242,11 @@ __device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in
         const uint32_t ip_limit = n - 15;
         bool reprobe = false;
         uint32_t kb = 0;
+        // Probes tried per batch.  Right after a match the next hit is usually a few positions away (dense-match
+        // data: text), and every probe of a batch costs a table sector from HBM whether or not the batch gets that
+        // far -- ncu on text: 11 MB of DRAM reads per 64 KiB block -- so the first batch after a match is w0 wide
+        // and only a miss widens it to 32.  Pure scheduling: the table sees the same sequence of reads and writes.
+        uint32_t width = SNP_WARP;
         for (;;) {
             uint32_t p, nip;
             bool term = false;
@@ -255,8 +260,9 @@ __device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in
                 nip = p + (s >> 20);
                 term = nip > ip_limit || k >= SNP_SCHED_LEN;  // :323-327
             }
-            const unsigned terms = __ballot_sync(SNP_FULL, term);
-            const unsigned live = terms ? ((1u << (__ffs(terms) - 1)) - 1u) : SNP_FULL;
+            const unsigned wmask = 0xffffffffu >> (SNP_WARP - width);
+            const unsigned terms = __ballot_sync(SNP_FULL, term) & wmask;
+            const unsigned live = (terms ? ((1u << (__ffs(terms) - 1)) - 1u) : SNP_FULL) & wmask;
             const bool is_live = (live >> lane) & 1;
             const uint32_t x = is_live ? ld_le32(in + p) : 0u;
             const uint32_t h = is_live ? (table_hash<HASH_MODE>(x, mask, lut) >> 1) : (0x10000u + lane);
@@ -285,8 +291,9 @@ __device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in
             __syncwarp();
             if (!hits) {
                 if (terms) break;
-                kb += reprobe ? 31u : 32u;
+                kb += width - (reprobe ? 1u : 0u);
                 reprobe = false;
+                width = SNP_WARP;
                 continue;
             }
             uint32_t ip = __shfl_sync(SNP_FULL, p, f);
@@ -304,6 +311,7 @@ __device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in
             __syncwarp();
             reprobe = true;
             kb = 0;
+            width = w0;
         }
     }
     if (next_emit < n) emit_literal_v1(o, in + next_emit, n - next_emit, lane);  // :406-411
@@ -462,6 +470,8 @@ k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
     const unsigned warp = threadIdx.x / SNP_WARP;
     const unsigned lane = lane_id();
     uint32_t *table = tables + ((size_t)blockIdx.x * warps + warp) * 16384;
+    const uint32_t w0 = min(max((uint32_t)frag_mode >> 8, 1u), (uint32_t)SNP_WARP);  // first-batch width (bits 8..)
+    frag_mode &= 1;
 
     for (;;) {
         unsigned long long item = 0;
@@ -483,7 +493,7 @@ k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
             }
             if (n > 0) {
                 if (VARIANT == 4) compress_fragment_v4<HASH_MODE>(in, n, o, table, lut, sched);
-                else compress_fragment_v3<HASH_MODE>(in, n, o, table, lut, sched);
+                else compress_fragment_v3<HASH_MODE>(in, n, o, table, lut, sched, w0);
             }
             if (o.pos > o.cap) st = SNP_OUTPUT_TOO_SMALL;  // SnappyCompressor.cs:63-68
         }

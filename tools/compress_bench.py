@@ -45,6 +45,8 @@ def main():
         env = {"SNP_COMP_CTAS_PER_SM": "8", "SNP_COMP_L2_PERSIST_MB": "0", "SNP_COMP_KERNEL": "3"}
         if v.startswith("k"):  # "k2" = SNP_COMP_KERNEL=2
             env["SNP_COMP_KERNEL"] = v[1:]
+        elif v.startswith("w"):  # "w8" = SNP_COMP_FIRST_WIDTH=8
+            env["SNP_COMP_FIRST_WIDTH"] = v[1:]
         else:
             ctas, _, mb = v.partition(":")
             env.update({"SNP_COMP_CTAS_PER_SM": ctas, "SNP_COMP_L2_PERSIST_MB": mb or "0"})
