@@ -115,7 +115,7 @@ struct snp_ctx {
     DevBuf d_in, d_out, d_meta, d_tmp;
     DevBuf d_tables;           // k_compress_v3: one 32 KiB hash table per resident warp
     int comp_ctas_per_sm = 8;  // SNP_COMP_CTAS_PER_SM (x 8 warps)
-    int comp_first_width = 8;  // SNP_COMP_FIRST_WIDTH: probes in the first batch after a match (k_compress_v3; 32 = old)
+    int comp_first_width = 16;  // SNP_COMP_FIRST_WIDTH: probes in the first batch after a match (k_compress_v3; 32 = fixed width)
     size_t comp_l2_persist_bytes = 0;  // SNP_COMP_L2_PERSIST_MB: L2 set aside for the compressor's hash tables (0 = off)
     size_t l2_window_max = 0;
     unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
@@ -744,7 +744,7 @@ int snp_create(int device, snp_ctx **out) {
     c->v6_wave = (size_t)std::max(1, env_int("SNP_V6_WAVE", 262144));
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
-    c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 8)));
+    c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));
     {
         const size_t want = (size_t)std::max(0, env_int("SNP_COMP_L2_PERSIST_MB", 0)) << 20;
         c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
