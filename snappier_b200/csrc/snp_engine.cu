@@ -116,8 +116,6 @@ struct snp_ctx {
     DevBuf d_tables;           // k_compress_v3: one 32 KiB hash table per resident warp
     int comp_ctas_per_sm = 8;  // SNP_COMP_CTAS_PER_SM (x 8 warps)
     int comp_first_width = 16;  // SNP_COMP_FIRST_WIDTH: probes in the first batch after a match (k_compress_v3; 32 = fixed width)
-    size_t comp_l2_persist_bytes = 0;  // SNP_COMP_L2_PERSIST_MB: L2 set aside for the compressor's hash tables (0 = off)
-    size_t l2_window_max = 0;
     unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
     unsigned counter_seq = 0;
     static constexpr int kSlots = 4;  // host-mode pipeline depth (H2D | kernel | D2H overlap)
@@ -289,20 +287,6 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
         unsigned grid3 = (unsigned)std::min(ctas3, (size_t)c->sm_count * cps);
         const size_t table_bytes = (size_t)c->sm_count * cps * wpc * 65536;
         if ((rc = c->d_tables.reserve(table_bytes))) return rc;
-        // SNP_COMP_L2_PERSIST: pin the hash tables in the 126 MB L2 (persisting access-policy window on the launch
-        // stream) so that the streaming input / output cannot evict them; restored after the launch.
-        bool window_set = false;
-        if (c->comp_l2_persist_bytes) {
-            cudaStreamAttrValue av{};
-            av.accessPolicyWindow.base_ptr = c->d_tables.p;
-            av.accessPolicyWindow.num_bytes = std::min(table_bytes, c->l2_window_max);
-            av.accessPolicyWindow.hitRatio =
-                (float)std::min(1.0, (double)c->comp_l2_persist_bytes / (double)av.accessPolicyWindow.num_bytes);
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            window_set = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
-            if (!window_set) cudaGetLastError();
-        }
 #define SNP_LAUNCH_C3(H, V)                                                                                  \
     snp::k_compress_v3<H, V><<<grid3, wpc * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap, \
                                                               out_len, status, n,                                  \
@@ -316,11 +300,6 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
             else SNP_LAUNCH_C3(SNP_HASH_MUL, 4);
         }
 #undef SNP_LAUNCH_C3
-        if (window_set) {
-            cudaStreamAttrValue av{};
-            av.accessPolicyWindow.num_bytes = 0;
-            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
-        }
     } else {
         unsigned long long *ctr;
         if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
@@ -745,15 +724,6 @@ int snp_create(int device, snp_ctx **out) {
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));
-    {
-        const size_t want = (size_t)std::max(0, env_int("SNP_COMP_L2_PERSIST_MB", 0)) << 20;
-        c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
-        if (want && prop.persistingL2CacheMaxSize > 0 && c->l2_window_max) {
-            const size_t lim = std::min(want, (size_t)prop.persistingL2CacheMaxSize);
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess) c->comp_l2_persist_bytes = lim;
-            else cudaGetLastError();
-        }
-    }
     *out = c.release();
     return SNP_OK;
 }

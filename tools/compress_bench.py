@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Compress throughput of engine settings (diagnostics): python tools/compress_bench.py [--blocks 32768]
-Variants are "ctas[:persist_mb]" = SNP_COMP_CTAS_PER_SM and SNP_COMP_L2_PERSIST_MB (e.g. 8,4,2:96) or "kN" = SNP_COMP_KERNEL=N."""
+Variants: "N" = SNP_COMP_CTAS_PER_SM, "kN" = SNP_COMP_KERNEL, "wN" = SNP_COMP_FIRST_WIDTH."""
 from __future__ import annotations
 
 import argparse
@@ -19,7 +19,7 @@ import class_bench as CB  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blocks", type=int, default=1 << 15)
-    ap.add_argument("--variants", default="8,4,2,8:96,4:96,3:96,2:96,1:96")
+    ap.add_argument("--variants", default="8,4,2,w32,w8")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "compress_bench.json"))
     args = ap.parse_args()
     import torch
@@ -42,14 +42,13 @@ def main():
     res = {}
     ref_len = {}
     for v in args.variants.split(","):
-        env = {"SNP_COMP_CTAS_PER_SM": "8", "SNP_COMP_L2_PERSIST_MB": "0", "SNP_COMP_KERNEL": "3"}
+        env = {"SNP_COMP_CTAS_PER_SM": "8", "SNP_COMP_KERNEL": "3"}
         if v.startswith("k"):  # "k2" = SNP_COMP_KERNEL=2
             env["SNP_COMP_KERNEL"] = v[1:]
         elif v.startswith("w"):  # "w8" = SNP_COMP_FIRST_WIDTH=8
             env["SNP_COMP_FIRST_WIDTH"] = v[1:]
         else:
-            ctas, _, mb = v.partition(":")
-            env.update({"SNP_COMP_CTAS_PER_SM": ctas, "SNP_COMP_L2_PERSIST_MB": mb or "0"})
+            env["SNP_COMP_CTAS_PER_SM"] = v
         eng = CB.engine_with(env)
         row = {}
         for name, raw in data.items():
