@@ -108,8 +108,9 @@ def test_emu_v6_corpus_and_synthetic_blocks(oracle, fixtures, emu, tmp_path):
     check(oracle, emu, items, tmp_path, seed=1)
 
 
-def test_emu_v6_handmade_tag_forms(oracle, emu, tmp_path):
-    """COPY4, multi-byte literal lengths, literals around the 64 / 128-byte path boundaries, offsets around 16."""
+def handmade_tag_forms() -> list[bytes]:
+    """Hand-assembled blocks: COPY4, multi-byte literal lengths, literals around the 64 / 128-byte path boundaries,
+    offsets around 16, literals > 64 bytes at every slot position, chained near / far copies."""
     rng = np.random.default_rng(12)
     lit = rng.integers(0, 256, size=70000, dtype=np.uint8).tobytes()
 
@@ -181,7 +182,12 @@ def test_emu_v6_handmade_tag_forms(oracle, emu, tmp_path):
             body += copy(off, ln)
             total += ln
     items.append(varint(total) + bytes(body))
-    check(oracle, emu, items, tmp_path, seed=2)
+    return items
+
+
+
+def test_emu_v6_handmade_tag_forms(oracle, emu, tmp_path):
+    check(oracle, emu, handmade_tag_forms(), tmp_path, seed=2)
 
 
 def test_emu_v6_fuzz(oracle, emu, tmp_path):

@@ -457,6 +457,32 @@ def test_v6_waves_work_stealing_and_fallback(oracle, fixtures):
     e6.close()
 
 
+def test_v6_handmade_tag_forms_and_fuzz(oracle):
+    """Kernel 6 on the hand-assembled tag forms the emulator tests use (COPY4, literal-length forms, literals > 64
+    bytes at every slot position, every offset 1..40 x lengths around the 16-byte trips) and on mutated blocks:
+    status and bytes equal the oracle's."""
+    from snappier_b200.batch import decompress_many
+    from tests.test_emu_v6 import handmade_tag_forms
+    e6 = _engine_with({"SNP_DECOMP_KERNEL": "6", "SNP_V6_MIN_ITEMS": "1"})
+    items = handmade_tag_forms()
+    rng = np.random.default_rng(4)
+    for b in list(items[5:40]):
+        m = bytearray(b)
+        for _ in range(3):
+            m[int(rng.integers(0, len(m)))] = int(rng.integers(0, 256))
+        items.append(bytes(m))
+    caps = []
+    for b in items:
+        st, n = oracle.uncompressed_length(b)
+        caps.append(min(n, 1 << 20) if st == 0 else 0)
+    got, status = decompress_many(e6, items, caps)
+    for i, b in enumerate(items):
+        st, dec = oracle.decompress(b, cap=caps[i])
+        assert status[i] == st, (i, status[i], st)
+        assert got[i] == dec, i
+    e6.close()
+
+
 def test_single_call_api_is_thread_safe(oracle):
     """Snappy.* are static and re-entrant (SURVEY 8(b) "Threading"): concurrent calls from several
     threads, each on its lazily created thread-local context, all give oracle bytes."""
