@@ -18,6 +18,7 @@
 #include "snp_common.cuh"
 #include "snp_compress_v1.cuh"
 #include "snp_compress_v2.cuh"
+#include "snp_compress_v5.cuh"
 #include "snp_decompress_v1.cuh"
 #include "snp_decompress_v2.cuh"
 #include "snp_decompress_v3.cuh"
@@ -277,6 +278,23 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
         else
             snp::k_compress_v1<SNP_HASH_MUL><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
                 in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode);
+    } else if (c->comp_kernel == 5) {
+        // two blocks per warp: one per half-warp (snp_compress_v5.cuh)
+        unsigned long long *ctr;
+        if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
+        constexpr int W = 16;
+        const int gpc = 256 / W;  // lane groups (= blocks in flight) per CTA
+        const int cps = c->comp_ctas_per_sm;
+        const size_t ctas5 = (n + gpc - 1) / gpc;
+        const unsigned grid5 = (unsigned)std::min(ctas5, (size_t)c->sm_count * cps);
+        if ((rc = c->d_tables.reserve((size_t)c->sm_count * cps * gpc * 65536))) return rc;
+        const int fm = frag_mode | (c->comp_first_width << 8);
+        if (hash_mode == SNP_HASH_CRC32C)
+            snp::k_compress_v5<SNP_HASH_CRC32C, W><<<grid5, 256, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap,
+                                                                        out_len, status, n, fm, ctr, (uint32_t *)c->d_tables.p);
+        else
+            snp::k_compress_v5<SNP_HASH_MUL, W><<<grid5, 256, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap,
+                                                                     out_len, status, n, fm, ctr, (uint32_t *)c->d_tables.p);
     } else if (c->comp_kernel >= 3) {
         // hash tables in global memory (L2): occupancy no longer capped by shared memory
         unsigned long long *ctr;
