@@ -111,7 +111,8 @@ struct snp_ctx {
     cudaEvent_t v6_done = nullptr;  // orders users of d_v6 that arrive on different streams
     cudaStream_t v6_last_stream = nullptr;
     bool v6_used = false;
-    int comp_kernel = 3;    // SNP_COMP_KERNEL (1 = baseline, 2 = smem tables, 3 = L2 tables, 4 = 3 + register window;
+    int comp_kernel = 3;    // SNP_COMP_KERNEL (1 = baseline, 2 = smem tables, 3 = L2 tables, 4 = 3 + register window,
+                            // 5 = two blocks per warp (half-warps): measured 10-15 % slower than 3, DESIGN.md 4.6;
                             // 4 measured equal to 3: the kernel is bound by random table sectors)
     DevBuf d_in, d_out, d_meta, d_tmp;
     DevBuf d_tables;           // k_compress_v3: one 32 KiB hash table per resident warp
