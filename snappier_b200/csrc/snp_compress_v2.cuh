@@ -223,7 +223,9 @@ k_compress_v2(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
 // that cannot match; surviving candidates are still verified against the real bytes.
 __device__ __forceinline__ uint32_t fp16(uint32_t x) { return (x * 0x9E3779B1u) >> 16; }
 
-template <int HASH_MODE>
+// FP = false: the reference's plain 16-bit entries (32 KiB per table, no fingerprint filter): half the table footprint
+// in L2 at the price of one candidate load per live probe.
+template <int HASH_MODE, bool FP = true>
 __device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in, uint32_t n, OutCursor &o,
                                                   uint32_t *table, const uint16_t *lut, const uint32_t *sched, uint32_t w0) {
     const unsigned lane = lane_id();
@@ -233,10 +235,10 @@ __device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in
     uint32_t next_emit = 0;
     if (n >= 15) {  // Constants.InputMarginBytes, SnappyCompressor.cs:190
         {  // HashTable.cs:52: "zero" = position 0, whose bytes are in[0..3]
-            const uint32_t e0 = fp16(ld_le32(in)) << 16;
+            const uint32_t e0 = FP ? fp16(ld_le32(in)) << 16 : 0u;
             uint4 z = make_uint4(e0, e0, e0, e0);
             uint4 *t4 = reinterpret_cast<uint4 *>(table);
-            for (int i = lane; i < tsize / 4; i += SNP_WARP) __stcg(t4 + i, z);
+            for (int i = lane; i < tsize / (FP ? 4 : 8); i += SNP_WARP) __stcg(t4 + i, z);
             __syncwarp();
         }
         const uint32_t ip_limit = n - 15;
@@ -279,16 +281,23 @@ __device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in
                     cand = p_src;
                     hit = x_src == x;
                 } else {
-                    const uint32_t e = __ldcg(table + h);
-                    cand = e & 0xffffu;
-                    if ((e >> 16) == fp16(x)) hit = ld_le32(in + cand) == x;
+                    if (FP) {
+                        const uint32_t e = __ldcg(table + h);
+                        cand = e & 0xffffu;
+                        if ((e >> 16) == fp16(x)) hit = ld_le32(in + cand) == x;
+                    } else {
+                        cand = __ldcg(reinterpret_cast<const uint16_t *>(table) + h);
+                        hit = ld_le32(in + cand) == x;
+                    }
                 }
             }
             const unsigned hits = __ballot_sync(SNP_FULL, hit);
             const int f = __ffs(hits) - 1;
             const unsigned commit = hits ? (live & (0xffffffffu >> (31 - f))) : live;
-            if (((commit >> lane) & 1) && (same & commit & ~lt & ~(1u << lane)) == 0)
-                __stcg(table + h, p | (fp16(x) << 16));
+            if (((commit >> lane) & 1) && (same & commit & ~lt & ~(1u << lane)) == 0) {
+                if (FP) __stcg(table + h, p | (fp16(x) << 16));
+                else __stcg(reinterpret_cast<uint16_t *>(table) + h, (uint16_t)p);
+            }
             __syncwarp();
             if (!hits) {
                 if (terms) break;
@@ -307,7 +316,9 @@ __device__ __noinline__ void compress_fragment_v3(const uint8_t *__restrict__ in
             if (ip >= ip_limit) break;  // :381-384
             if (lane == 0) {            // :393-394
                 const uint32_t x1 = ld_le32(in + ip - 1);
-                __stcg(table + (table_hash<HASH_MODE>(x1, mask, lut) >> 1), (ip - 1) | (fp16(x1) << 16));
+                const uint32_t h1 = table_hash<HASH_MODE>(x1, mask, lut) >> 1;
+                if (FP) __stcg(table + h1, (ip - 1) | (fp16(x1) << 16));
+                else __stcg(reinterpret_cast<uint16_t *>(table) + h1, (uint16_t)(ip - 1));
             }
             __syncwarp();
             reprobe = true;
@@ -494,6 +505,7 @@ k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
             }
             if (n > 0) {
                 if (VARIANT == 4) compress_fragment_v4<HASH_MODE>(in, n, o, table, lut, sched);
+                else if (VARIANT == 6) compress_fragment_v3<HASH_MODE, false>(in, n, o, table, lut, sched, w0);
                 else compress_fragment_v3<HASH_MODE>(in, n, o, table, lut, sched, w0);
             }
             if (o.pos > o.cap) st = SNP_OUTPUT_TOO_SMALL;  // SnappyCompressor.cs:63-68

@@ -314,6 +314,9 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
         if (c->comp_kernel == 3) {
             if (hash_mode == SNP_HASH_CRC32C) SNP_LAUNCH_C3(SNP_HASH_CRC32C, 3);
             else SNP_LAUNCH_C3(SNP_HASH_MUL, 3);
+        } else if (c->comp_kernel == 6) {  // plain 16-bit table entries
+            if (hash_mode == SNP_HASH_CRC32C) SNP_LAUNCH_C3(SNP_HASH_CRC32C, 6);
+            else SNP_LAUNCH_C3(SNP_HASH_MUL, 6);
         } else {
             if (hash_mode == SNP_HASH_CRC32C) SNP_LAUNCH_C3(SNP_HASH_CRC32C, 4);
             else SNP_LAUNCH_C3(SNP_HASH_MUL, 4);

@@ -380,7 +380,7 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     c1, s1 = compress_many(e1, blocks, 0)
     c2, s2 = compress_many(e2, blocks, 0)
     assert c1 == c2 and not s1.any() and not s2.any()
-    for variant in ("2", "4", "5"):  # shared-memory tables; L2 tables + register window; two blocks per warp (half-warps)
+    for variant in ("2", "4", "5", "6"):  # smem tables; L2 tables + register window; half-warps; 16-bit L2 tables
         ev = _engine_with({"SNP_COMP_KERNEL": variant})
         for mode in (0, 1):
             cv, sv = compress_many(ev, blocks, mode)

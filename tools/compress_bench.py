@@ -43,8 +43,11 @@ def main():
     ref_len = {}
     for v in args.variants.split(","):
         env = {"SNP_COMP_CTAS_PER_SM": "8", "SNP_COMP_KERNEL": "3"}
-        if v.startswith("k"):  # "k2" = SNP_COMP_KERNEL=2
-            env["SNP_COMP_KERNEL"] = v[1:]
+        if v.startswith("k"):  # "k2" = SNP_COMP_KERNEL=2, "k6c4" = kernel 6 at 4 CTAs per SM
+            k, _, cc = v[1:].partition("c")
+            env["SNP_COMP_KERNEL"] = k
+            if cc:
+                env["SNP_COMP_CTAS_PER_SM"] = cc
         elif v.startswith("w"):  # "w8" = SNP_COMP_FIRST_WIDTH=8
             env["SNP_COMP_FIRST_WIDTH"] = v[1:]
         else:
