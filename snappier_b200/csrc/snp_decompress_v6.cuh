@@ -498,6 +498,8 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                     bool src_in = is_lit;                        // the source is the input stream
                     uint32_t sp = is_lit ? ski + val : s_pos;    // first source byte (input or P coordinates)
                     bool single = fast;                          // no waiting needed: one round
+                    bool exact = false;                          // readiness from needm instead of the prefix frontier
+                    unsigned needm = 0;                          // lanes whose output this tag's source overlaps
                     if (!fast) {
                         // (a hop costs ~45 instructions: worth it for chains -- records, markup --, not for the one or
                         //  two dependent tags of a text group, which simply take a second round)
@@ -531,12 +533,34 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                             }
                         }
                         const bool waits = mine && !src_in && (periodic ? rd > ss : sp + len > ss);
-                        single = __ballot_sync(SNP_FULL, waits) == 0;
+                        const unsigned wm = __ballot_sync(SNP_FULL, waits);
+                        single = wm == 0;
+                        // Exact readiness: the prefix frontier makes a dependent tag wait for EVERY earlier tag of the
+                        // group; with several waiting tags it pays to find, once, the lanes whose output a tag really
+                        // reads (the tags are contiguous in the output, so that is a lane interval).
+                        if (__popc(wm) >= 3) {
+                            const uint32_t lo_p = periodic ? pbase : sp;                 // first / last source byte (P)
+                            const uint32_t hi_p = periodic ? rd - 1 : sp + len - 1;
+                            uint32_t ja = 0, jb = 0;
+#pragma unroll
+                            for (uint32_t step = 16; step; step >>= 1) {
+                                const uint32_t da = __shfl_sync(SNP_FULL, d, ja + step);
+                                const uint32_t db = __shfl_sync(SNP_FULL, d, jb + step);
+                                if (da <= lo_p) ja += step;
+                                if (db <= hi_p) jb += step;
+                            }
+                            // lanes ja .. jb produce [lo_p, hi_p]; everything below t0 is final already
+                            const unsigned upto = 0xffffffffu >> (31 - jb);
+                            needm = waits ? (upto & ~((1u << ja) - 1u) & ~(1u << lane)) : 0u;
+                            exact = true;
+                        }
                     }
                     while (pending) {
                         SNP6_STAT(rounds, 1);
                         bool ready = mine;
-                        if (!single) {
+                        if (exact) {
+                            ready = mine && ((pending >> lane) & 1u) && (needm & pending) == 0;
+                        } else if (!single) {
                             const unsigned f = __ffs(pending) - 1;
                             const uint32_t F = __shfl_sync(SNP_FULL, d, f);  // every byte below F is final
                             ready = mine && ((pending >> lane) & 1u) && (src_in || (periodic ? rd : sp + len) <= F);
