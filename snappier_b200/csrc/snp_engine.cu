@@ -115,7 +115,10 @@ struct snp_ctx {
                             // 5 = two blocks per warp (half-warps): measured 10-15 % slower than 3, DESIGN.md 4.6;
                             // 4 measured equal to 3: the kernel is bound by random table sectors)
     DevBuf d_in, d_out, d_meta, d_tmp;
-    DevBuf d_tables;           // k_compress_v3: one 32 KiB hash table per resident warp
+    DevBuf d_tables;           // k_compress_v3: one 64 KiB hash table slice per resident warp
+    cudaEvent_t tables_done = nullptr;  // orders compress launches that arrive on different streams (shared d_tables)
+    cudaStream_t tables_last_stream = nullptr;
+    bool tables_used = false;
     int comp_ctas_per_sm = 8;  // SNP_COMP_CTAS_PER_SM (x 8 warps)
     int comp_first_width = 16;  // SNP_COMP_FIRST_WIDTH: probes in the first batch after a match (k_compress_v3; 32 = fixed width)
     unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
@@ -270,6 +273,15 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
     if (n == 0) return SNP_OK;
     int rc = ctx_set_attrs(c);
     if (rc) return rc;
+    // The L2-table kernels share ONE table buffer (a slice per resident CTA/warp), and the host-mode pipeline launches
+    // consecutive chunks on different streams: a chunk's CTAs could start in the tail of the previous launch and clear a
+    // slice that one of its warps is still using.  Launches on different streams are therefore chained with an event
+    // (each launch fills the GPU by itself, so nothing is lost; the copies of the chunks still overlap).
+    const bool shared_tables = c->comp_kernel >= 3;
+    if (shared_tables) {
+        if (!c->tables_done) CU(cudaEventCreateWithFlags(&c->tables_done, cudaEventDisableTiming));
+        if (c->tables_used && c->tables_last_stream != s) CU(cudaStreamWaitEvent(s, c->tables_done, 0));
+    }
     size_t ctas = (n + kCompWarps - 1) / kCompWarps;
     unsigned grid = (unsigned)(ctas < (size_t)c->sm_count ? ctas : (size_t)c->sm_count);
     if (c->comp_kernel == 1) {
@@ -336,6 +348,11 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
     }
     c->launches++;
     CU(cudaGetLastError());
+    if (shared_tables) {
+        CU(cudaEventRecord(c->tables_done, s));
+        c->tables_last_stream = s;
+        c->tables_used = true;
+    }
     return SNP_OK;
 }
 
@@ -759,6 +776,7 @@ void snp_destroy(snp_ctx *c) {
     }
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->v6_done) cudaEventDestroy(c->v6_done);
+    if (c->tables_done) cudaEventDestroy(c->tables_done);
     for (auto &sl : c->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream), cudaStreamDestroy(sl.stream);
         if (sl.meta_ready) cudaEventDestroy(sl.meta_ready);

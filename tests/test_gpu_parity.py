@@ -483,6 +483,25 @@ def test_v6_handmade_tag_forms_and_fuzz(oracle):
     e6.close()
 
 
+def test_host_mode_compress_many_chunks_in_flight(engine, oracle):
+    """Host-mode batches flow through a 4-slot pipeline on 4 streams (16 384 items per chunk).  The L2-table compress
+    kernels share one table buffer, so consecutive chunks must not overlap on the GPU: 50 000 small blocks (short
+    kernels, many chunks) must still be bit-exact."""
+    from snappier_b200.batch import compress_many, decompress_many
+    blocks = H.synthetic_blocks(321, 50, size=3000)
+    items = [blocks[i % 50][(i * 7) % 500:] for i in range(50000)]
+    comp, st = compress_many(engine, items, 0)
+    assert not st.any()
+    want = {}
+    for i in range(0, 50000, 97):
+        key = (i % 50, (i * 7) % 500)
+        if key not in want:
+            want[key] = oracle.compress(items[i])[1]
+        assert comp[i] == want[key], i
+    back, st2 = decompress_many(engine, comp)
+    assert not st2.any() and back == items
+
+
 def test_single_call_api_is_thread_safe(oracle):
     """Snappy.* are static and re-entrant (SURVEY 8(b) "Threading"): concurrent calls from several
     threads, each on its lazily created thread-local context, all give oracle bytes."""
