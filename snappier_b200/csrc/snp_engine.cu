@@ -120,6 +120,7 @@ struct snp_ctx {
     cudaStream_t tables_last_stream = nullptr;
     bool tables_used = false;
     int comp_ctas_per_sm = 8;  // SNP_COMP_CTAS_PER_SM (x 8 warps)
+    uint64_t host_chunk_bytes = 128ull << 20;  // host-mode pipeline: bytes per chunk (SNP_HOST_CHUNK_MB)
     int comp_first_width = 16;  // SNP_COMP_FIRST_WIDTH: probes in the first batch after a match (k_compress_v3; 32 = fixed width)
     unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
     unsigned counter_seq = 0;
@@ -512,7 +513,7 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
         if (!sl.stream) CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         if (!sl.meta_ready) CU(cudaEventCreateWithFlags(&sl.meta_ready, cudaEventDisableTiming));
     }
-    constexpr uint64_t kChunkBytes = 128ull << 20;  // per-chunk output span target
+    const uint64_t kChunkBytes = c->host_chunk_bytes;  // per-chunk output span target (SNP_HOST_CHUNK_MB)
     constexpr size_t kChunkItems = 16384;
     Chunk prev;
     bool have_prev = false;
@@ -763,6 +764,7 @@ int snp_create(int device, snp_ctx **out) {
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));
+    c->host_chunk_bytes = (uint64_t)std::max(1, env_int("SNP_HOST_CHUNK_MB", 128)) << 20;
     *out = c.release();
     return SNP_OK;
 }
