@@ -120,6 +120,7 @@ struct snp_ctx {
     cudaStream_t tables_last_stream = nullptr;
     bool tables_used = false;
     int comp_ctas_per_sm = 8;  // SNP_COMP_CTAS_PER_SM (x 8 warps)
+    int host_early_d2h = 1;  // SNP_HOST_EARLY_D2H: enqueue the payload copy of dense decompress chunks behind the kernel
     uint64_t host_chunk_bytes = 128ull << 20;  // host-mode pipeline: bytes per chunk (SNP_HOST_CHUNK_MB)
     int comp_first_width = 16;  // SNP_COMP_FIRST_WIDTH: probes in the first batch after a match (k_compress_v3; 32 = fixed width)
     unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
@@ -434,10 +435,12 @@ struct Chunk {
     size_t a = 0, b = 0;  // item range
     Span si, so;
     int slot = 0;
+    bool early_d2h = false;  // the payload copy was already enqueued in phase 1
 };
 
-int chunk_phase1(snp_ctx *c, const Chunk &ck, bool compress, const uint8_t *in_base, const uint64_t *in_off,
-                 const uint32_t *in_len, const uint64_t *out_off, const uint32_t *out_cap, uint32_t hash_mode) {
+int chunk_phase1(snp_ctx *c, Chunk &ck, bool compress, const uint8_t *in_base, const uint64_t *in_off,
+                 const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap,
+                 uint32_t hash_mode) {
     snp_ctx::Slot &sl = c->slots[ck.slot];
     cudaStream_t s = sl.stream;
     const size_t n = ck.b - ck.a;
@@ -477,6 +480,18 @@ int chunk_phase1(snp_ctx *c, const Chunk &ck, bool compress, const uint8_t *in_b
     // out_len + status are contiguous: one D2H into the pinned mirror (copied to the caller in phase 2)
     CU(cudaMemcpyAsync(hm + ml.out_len, dm + ml.out_len, ml.bytes - ml.out_len, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(sl.meta_ready, s));
+    // Decompress into back-to-back capacity regions (the usual dense layout): the whole output span lies inside the
+    // caller's regions, so its copy can be enqueued right behind the kernel instead of after a host round trip for
+    // the produced lengths (bytes of a region beyond out_len are unspecified, as in the device-mode call).
+    ck.early_d2h = false;
+    if (!compress && c->host_early_d2h) {
+        bool dense = true;
+        for (size_t i = ck.a; i + 1 < ck.b && dense; i++) dense = out_off[i + 1] == out_off[i] + out_cap[i];
+        if (dense && ck.so.hi > ck.so.lo) {
+            CU(cudaMemcpyAsync(out_base + ck.so.lo, sl.d_out.p, ck.so.hi - ck.so.lo, cudaMemcpyDeviceToHost, s));
+            ck.early_d2h = true;
+        }
+    }
     return SNP_OK;
 }
 
@@ -492,6 +507,7 @@ int chunk_phase2(snp_ctx *c, const Chunk &ck, uint8_t *out_base, const uint64_t 
         memcpy(out_len + ck.a, hm + ml.out_len, (ck.b - ck.a) * 4);
         memcpy(status + ck.a, hm + ml.status, (ck.b - ck.a) * 4);
     }
+    if (ck.early_d2h) return SNP_OK;
     size_t i = ck.a;
     while (i < ck.b) {
         size_t j = i;
@@ -534,7 +550,7 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
         }
         ck.b = b;
         ck.si.lo = ilo, ck.si.hi = ihi, ck.so.lo = olo, ck.so.hi = ohi;
-        rc = chunk_phase1(c, ck, compress, in_base, in_off, in_len, out_off, out_cap, hash_mode);
+        rc = chunk_phase1(c, ck, compress, in_base, in_off, in_len, out_base, out_off, out_cap, hash_mode);
         if (rc == SNP_OK && have_prev) rc = chunk_phase2(c, prev, out_base, out_off, out_cap, out_len, status);
         prev = ck;
         have_prev = true;
@@ -765,6 +781,7 @@ int snp_create(int device, snp_ctx **out) {
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));
     c->host_chunk_bytes = (uint64_t)std::max(1, env_int("SNP_HOST_CHUNK_MB", 128)) << 20;
+    c->host_early_d2h = env_int("SNP_HOST_EARLY_D2H", 1);
     *out = c.release();
     return SNP_OK;
 }

@@ -24,8 +24,8 @@ off = c_off.cpu().numpy().astype(np.uint64)
 ln = c_len.cpu().numpy().astype(np.uint32)
 ooff = np.arange(n, dtype=np.uint64) * B.BLOCK
 ocap = np.full(n, B.BLOCK, np.uint32)
-for mb in (16, 32, 64, 128, 256, 512):
-    eng = CB.engine_with({"SNP_HOST_CHUNK_MB": str(mb)})
+for mb, early in ((128, 0), (128, 1), (64, 1), (256, 1), (32, 1)):
+    eng = CB.engine_with({"SNP_HOST_CHUNK_MB": str(mb), "SNP_HOST_EARLY_D2H": str(early)})
     for _ in range(2):
         eng.decompress_batch_host(h_in.numpy(), off, ln, h_out.numpy(), ooff, ocap)
     torch.cuda.synchronize()
@@ -33,5 +33,6 @@ for mb in (16, 32, 64, 128, 256, 512):
     for _ in range(5):
         ol, st = eng.decompress_batch_host(h_in.numpy(), off, ln, h_out.numpy(), ooff, ocap)
     dt = (time.perf_counter() - t0) / 5
-    print(f"chunk {mb:4d} MiB: {n * B.BLOCK / dt / 1e9:6.2f} GB/s  ok={not st.any()}", flush=True)
+    good = not st.any() and torch.equal(B.block_checksums(torch, h_out.to(dev), weights), sums[:n])
+    print(f"chunk {mb:4d} MiB early_d2h={early}: {n * B.BLOCK / dt / 1e9:6.2f} GB/s  ok={good}", flush=True)
     eng.close()
