@@ -13,6 +13,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <deque>
 #include <vector>
 
 #include "snp_common.cuh"
@@ -125,7 +126,7 @@ struct snp_ctx {
     int comp_first_width = 16;  // SNP_COMP_FIRST_WIDTH: probes in the first batch after a match (k_compress_v3; 32 = fixed width)
     unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
     unsigned counter_seq = 0;
-    static constexpr int kSlots = 4;  // host-mode pipeline depth (H2D | kernel | D2H overlap)
+    static constexpr int kSlots = 8;  // host-mode pipeline depth (H2D | kernel | D2H overlap)
     struct Slot {
         cudaStream_t stream = nullptr;
         cudaEvent_t meta_ready = nullptr;
@@ -531,8 +532,12 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
     }
     const uint64_t kChunkBytes = c->host_chunk_bytes;  // per-chunk output span target (SNP_HOST_CHUNK_MB)
     constexpr size_t kChunkItems = 16384;
-    Chunk prev;
-    bool have_prev = false;
+    // Phase 2 of a chunk (wait for its lengths / statuses, copy them to the caller, enqueue the payload copy when it was
+    // not enqueued early) runs kLag chunks behind phase 1: waiting for chunk k-1's kernel before enqueueing chunk k+1
+    // limited the pipeline to two chunks in flight, and a chunk's kernel is latency-bound (~1 ms: one block per warp).
+    // A slot is reused kSlots chunks later, i.e. kSlots - kLag chunks after its phase 2.
+    constexpr size_t kLag = snp_ctx::kSlots / 2;
+    std::deque<Chunk> pend;
     int rc = SNP_OK, k = 0;
     size_t a = 0;
     while (a < n && rc == SNP_OK) {
@@ -551,12 +556,17 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
         ck.b = b;
         ck.si.lo = ilo, ck.si.hi = ihi, ck.so.lo = olo, ck.so.hi = ohi;
         rc = chunk_phase1(c, ck, compress, in_base, in_off, in_len, out_base, out_off, out_cap, hash_mode);
-        if (rc == SNP_OK && have_prev) rc = chunk_phase2(c, prev, out_base, out_off, out_cap, out_len, status);
-        prev = ck;
-        have_prev = true;
+        pend.push_back(ck);
+        if (rc == SNP_OK && pend.size() > kLag) {
+            rc = chunk_phase2(c, pend.front(), out_base, out_off, out_cap, out_len, status);
+            pend.pop_front();
+        }
         a = b;
     }
-    if (rc == SNP_OK && have_prev) rc = chunk_phase2(c, prev, out_base, out_off, out_cap, out_len, status);
+    while (rc == SNP_OK && !pend.empty()) {
+        rc = chunk_phase2(c, pend.front(), out_base, out_off, out_cap, out_len, status);
+        pend.pop_front();
+    }
     for (auto &sl : c->slots) {
         cudaError_t e = cudaStreamSynchronize(sl.stream);
         if (e != cudaSuccess && rc == SNP_OK) rc = cuda_fail(e, "cudaStreamSynchronize(slot)", __LINE__);
