@@ -121,6 +121,9 @@ struct snp_ctx {
     cudaStream_t tables_last_stream = nullptr;
     bool tables_used = false;
     int comp_ctas_per_sm = 8;  // SNP_COMP_CTAS_PER_SM (x 8 warps)
+    int host_trace = 0;  // SNP_HOST_TRACE: print a per-chunk timeline of the host-mode pipeline (diagnostics)
+    struct TraceRow { cudaEvent_t e[5]; };
+    std::vector<TraceRow> trace;
     int host_early_d2h = 1;  // SNP_HOST_EARLY_D2H: enqueue the payload copy of dense decompress chunks behind the kernel
     uint64_t host_chunk_bytes = 128ull << 20;  // host-mode pipeline: bytes per chunk (SNP_HOST_CHUNK_MB)
     int comp_first_width = 16;  // SNP_COMP_FIRST_WIDTH: probes in the first batch after a match (k_compress_v3; 32 = fixed width)
@@ -463,8 +466,14 @@ int chunk_phase1(snp_ctx *c, Chunk &ck, bool compress, const uint8_t *in_base, c
     }
     // in_off .. out_cap are contiguous in the layout: one H2D for all input metadata
     CU(cudaMemcpyAsync(dm, hm, ml.out_len, cudaMemcpyHostToDevice, s));
+    cudaEvent_t tev[5] = {};
+    if (c->host_trace) {
+        for (auto &e : tev) CU(cudaEventCreate(&e));
+        CU(cudaEventRecord(tev[0], s));
+    }
     if (ck.si.hi > ck.si.lo)
         CU(cudaMemcpyAsync(sl.d_in.p, in_base + ck.si.lo, ck.si.hi - ck.si.lo, cudaMemcpyHostToDevice, s));
+    if (c->host_trace) CU(cudaEventRecord(tev[1], s));
     auto *d_in_off = (const uint64_t *)(dm + ml.in_off);
     auto *d_out_off = (const uint64_t *)(dm + ml.out_off);
     auto *d_in_len = (const uint32_t *)(dm + ml.in_len);
@@ -478,6 +487,7 @@ int chunk_phase1(snp_ctx *c, Chunk &ck, bool compress, const uint8_t *in_base, c
         rc = launch_decompress(c, s, (const uint8_t *)sl.d_in.p, d_in_off, d_in_len, (uint8_t *)sl.d_out.p,
                                d_out_off, d_out_cap, d_out_len, d_status, n, &sl.d_v6);
     if (rc) return rc;
+    if (c->host_trace) CU(cudaEventRecord(tev[2], s));
     // out_len + status are contiguous: one D2H into the pinned mirror (copied to the caller in phase 2)
     CU(cudaMemcpyAsync(hm + ml.out_len, dm + ml.out_len, ml.bytes - ml.out_len, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(sl.meta_ready, s));
@@ -489,10 +499,13 @@ int chunk_phase1(snp_ctx *c, Chunk &ck, bool compress, const uint8_t *in_base, c
         bool dense = true;
         for (size_t i = ck.a; i + 1 < ck.b && dense; i++) dense = out_off[i + 1] == out_off[i] + out_cap[i];
         if (dense && ck.so.hi > ck.so.lo) {
+            if (c->host_trace) CU(cudaEventRecord(tev[3], s));
             CU(cudaMemcpyAsync(out_base + ck.so.lo, sl.d_out.p, ck.so.hi - ck.so.lo, cudaMemcpyDeviceToHost, s));
+            if (c->host_trace) CU(cudaEventRecord(tev[4], s));
             ck.early_d2h = true;
         }
     }
+    if (c->host_trace) c->trace.push_back({tev[0], tev[1], tev[2], tev[3], tev[4]});
     return SNP_OK;
 }
 
@@ -570,6 +583,19 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
     for (auto &sl : c->slots) {
         cudaError_t e = cudaStreamSynchronize(sl.stream);
         if (e != cudaSuccess && rc == SNP_OK) rc = cuda_fail(e, "cudaStreamSynchronize(slot)", __LINE__);
+    }
+    if (c->host_trace && !c->trace.empty()) {  // ms since the first chunk's start: h2d begin/end, kernel end, d2h begin/end
+        cudaEvent_t t0 = c->trace[0].e[0];
+        for (size_t i = 0; i < c->trace.size(); i++) {
+            float v[5] = {};
+            for (int j = 0; j < 5; j++)
+                if (c->trace[i].e[j]) cudaEventElapsedTime(&v[j], t0, c->trace[i].e[j]);
+            fprintf(stderr, "chunk %3zu  h2d %7.3f..%7.3f  kernel ..%7.3f  d2h %7.3f..%7.3f\n", i, v[0], v[1], v[2], v[3], v[4]);
+        }
+        for (auto &r : c->trace)
+            for (auto e : r.e)
+                if (e) cudaEventDestroy(e);
+        c->trace.clear();
     }
     return rc;
 }
@@ -792,6 +818,7 @@ int snp_create(int device, snp_ctx **out) {
     c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));
     c->host_chunk_bytes = (uint64_t)std::max(1, env_int("SNP_HOST_CHUNK_MB", 128)) << 20;
     c->host_early_d2h = env_int("SNP_HOST_EARLY_D2H", 1);
+    c->host_trace = env_int("SNP_HOST_TRACE", 0);
     *out = c.release();
     return SNP_OK;
 }
