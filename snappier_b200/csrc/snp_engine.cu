@@ -125,7 +125,7 @@ struct snp_ctx {
     struct TraceRow { cudaEvent_t e[5]; };
     std::vector<TraceRow> trace;
     int host_early_d2h = 1;  // SNP_HOST_EARLY_D2H: enqueue the payload copy of dense decompress chunks behind the kernel
-    uint64_t host_chunk_bytes = 128ull << 20;  // host-mode pipeline: bytes per chunk (SNP_HOST_CHUNK_MB)
+    uint64_t host_chunk_bytes = 64ull << 20;   // host-mode pipeline: bytes per chunk (SNP_HOST_CHUNK_MB)
     int comp_first_width = 16;  // SNP_COMP_FIRST_WIDTH: probes in the first batch after a match (k_compress_v3; 32 = fixed width)
     unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
     unsigned counter_seq = 0;
@@ -559,10 +559,12 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
         ck.slot = k++ % snp_ctx::kSlots;
         uint64_t ilo = UINT64_MAX, ihi = 0, olo = UINT64_MAX, ohi = 0;
         size_t b = a;
+        // ramp up: the first chunks are small so that the first payload copy starts early (the D2H engine is the bottleneck)
+        const uint64_t limit = k <= 3 ? std::max<uint64_t>(kChunkBytes >> (4 - k), 1 << 20) : kChunkBytes;
         while (b < n && b - a < kChunkItems) {
             uint64_t nilo = std::min(ilo, in_off[b]), nihi = std::max(ihi, in_off[b] + in_len[b]);
             uint64_t nolo = std::min(olo, out_off[b]), nohi = std::max(ohi, out_off[b] + out_cap[b]);
-            if (b > a && (nohi - nolo > kChunkBytes || nihi - nilo > kChunkBytes)) break;
+            if (b > a && (nohi - nolo > limit || nihi - nilo > limit)) break;
             ilo = nilo, ihi = nihi, olo = nolo, ohi = nohi;
             b++;
         }
@@ -816,7 +818,7 @@ int snp_create(int device, snp_ctx **out) {
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));
-    c->host_chunk_bytes = (uint64_t)std::max(1, env_int("SNP_HOST_CHUNK_MB", 128)) << 20;
+    c->host_chunk_bytes = (uint64_t)std::max(1, env_int("SNP_HOST_CHUNK_MB", 64)) << 20;
     c->host_early_d2h = env_int("SNP_HOST_EARLY_D2H", 1);
     c->host_trace = env_int("SNP_HOST_TRACE", 0);
     *out = c.release();

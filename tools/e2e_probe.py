@@ -24,7 +24,7 @@ off = c_off.cpu().numpy().astype(np.uint64)
 ln = c_len.cpu().numpy().astype(np.uint32)
 ooff = np.arange(n, dtype=np.uint64) * B.BLOCK
 ocap = np.full(n, B.BLOCK, np.uint32)
-for mb, early in ((128, 1), (64, 1), (32, 1), (16, 1), (128, 0)):
+for mb, early in ((128, 1), (64, 1), (256, 1)):
     eng = CB.engine_with({"SNP_HOST_CHUNK_MB": str(mb), "SNP_HOST_EARLY_D2H": str(early)})
     for _ in range(2):
         eng.decompress_batch_host(h_in.numpy(), off, ln, h_out.numpy(), ooff, ocap)
