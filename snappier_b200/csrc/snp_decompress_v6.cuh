@@ -565,16 +565,9 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                             const uint32_t F = __shfl_sync(SNP_FULL, d, f);  // every byte below F is final
                             ready = mine && ((pending >> lane) & 1u) && (src_in || (periodic ? rd : sp + len) <= F);
                         }
-                        // few ready tags (the tail rounds of a dependency chain): cheaper one by one, cooperatively
-                        bool coop = false;
-                        if (!single) {
-                            const unsigned nr = __popc(__ballot_sync(SNP_FULL, ready));
-                            const uint32_t mxl = __reduce_max_sync(SNP_FULL, ready ? len : 0u);
-                            coop = nr * 40u <= 100u * ((mxl + 15u) >> 4);
-                        }
                         // ---- (S) one tag per lane, <= 16 bytes per trip -----------------------------
                         {
-                            uint32_t rem = (ready && !ctype && !coop) ? len : 0u;
+                            uint32_t rem = (ready && !ctype) ? len : 0u;
                             uint32_t cd = d - wbase;  // window offset of the next byte to write
                             uint32_t cs = periodic ? pbase + ph : sp;
                             while (__any_sync(SNP_FULL, rem != 0)) {
@@ -605,31 +598,19 @@ __device__ __noinline__ void decode_block_v6(const uint8_t *in, uint32_t n_in, u
                                 if (cs == pend) cs = pbase;  // periodic sources wrap at the end of the period
                             }
                         }
-                        // ---- (C) one tag at a time, a byte per lane: periods < 16 (CopyHelpers.IncrementalCopy's pattern
-                        //      replication), and every tag of a round with so few ready tags that 16-byte trips for a
-                        //      handful of lanes would cost more than ~40 instructions per tag
-                        unsigned cm = __ballot_sync(SNP_FULL, ready && (ctype || coop));
+                        // ---- (C) periods < 16 (CopyHelpers.IncrementalCopy's pattern replication)
+                        unsigned cm = fast ? 0u : __ballot_sync(SNP_FULL, ready && ctype);
                         while (cm) {
                             SNP6_STAT(ctags, 1);
                             const unsigned i = __ffs(cm) - 1;
                             cm &= cm - 1;
                             const uint32_t dd = __shfl_sync(SNP_FULL, d, i);
                             const uint32_t ll = __shfl_sync(SNP_FULL, len, i);
-                            const uint32_t oo = __shfl_sync(SNP_FULL, periodic ? val : 0u, i);  // period, 0 = plain copy
-                            const uint32_t sb = __shfl_sync(SNP_FULL, periodic ? pbase : sp, i);  // first source byte
-                            const uint32_t p0 = __shfl_sync(SNP_FULL, (periodic ? ph : 0u) | (src_in ? 0x80000000u : 0u), i);
-                            if (p0 >> 31) {  // the input stream (a literal, or a copy forwarded to one)
-                                const uint8_t *sbp = (const uint8_t *)in_v + sb;
-                                for (uint32_t k = lane; k < ll; k += SNP_WARP) sm->win[dd - wbase + k] = sbp[k];
-                            } else if (oo) {  // pattern = P in [sb, sb + oo), final
-                                const uint8_t *pat = sb >= hstart ? sm->win + (sb - wbase) : outA + sb;
-                                for (uint32_t k = lane; k < ll; k += SNP_WARP) sm->win[dd - wbase + k] = pat[(p0 + k) % oo];
-                            } else {  // older output: the window where it still holds it, global memory below
-                                for (uint32_t k = lane; k < ll; k += SNP_WARP) {
-                                    const uint32_t q = sb + k;
-                                    sm->win[dd - wbase + k] = q >= hstart ? sm->win[q - wbase] : outA[q];
-                                }
-                            }
+                            const uint32_t oo = __shfl_sync(SNP_FULL, val, i);
+                            const uint32_t pb = __shfl_sync(SNP_FULL, pbase, i);  // pattern = P in [pb, pb + oo), final
+                            const uint32_t p0 = __shfl_sync(SNP_FULL, ph, i);
+                            const uint8_t *pat = pb >= hstart ? sm->win + (pb - wbase) : outA + pb;
+                            for (uint32_t k = lane; k < ll; k += SNP_WARP) sm->win[dd - wbase + k] = pat[(p0 + k) % oo];
                         }
                         __syncwarp();  // this round's window bytes are visible to the next round / the flush
                         pending &= ~__ballot_sync(SNP_FULL, ready);
