@@ -76,6 +76,7 @@ __device__ __noinline__ int decompress_block_v1(const uint8_t *__restrict__ in, 
     return SNP_OK;
 }
 
+#ifndef SNP_EMU  // kernels: device only (the block functions above also run on tests/cpp/simt_emu.h)
 __global__ void __launch_bounds__(256)
 k_decompress_v1(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
                 const uint32_t *__restrict__ in_len, uint8_t *out_base,
@@ -108,5 +109,7 @@ __global__ void k_uncompressed_length(const uint8_t *__restrict__ in_base,
     ulen[i] = v;
     status[i] = st;
 }
+
+#endif  // !SNP_EMU
 
 }  // namespace snp

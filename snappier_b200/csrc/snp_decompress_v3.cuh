@@ -223,6 +223,7 @@ __device__ __noinline__ int decompress_block_v3(const uint8_t *__restrict__ in, 
 // Persistent launch: one CTA slot per (SM x resident CTA); every warp pulls the next block
 // index from a global counter, so cheap (incompressible) and expensive (text) blocks balance
 // across warps instead of leaving warp slots idle until the slowest warp of a CTA retires.
+#ifndef SNP_EMU
 __global__ void __launch_bounds__(256, SNP_V3_CTAS)
 k_decompress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
                 const uint32_t *__restrict__ in_len, uint8_t *out_base,
@@ -254,5 +255,7 @@ k_decompress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict_
         __syncwarp();
     }
 }
+
+#endif  // !SNP_EMU
 
 }  // namespace snp

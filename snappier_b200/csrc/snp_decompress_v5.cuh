@@ -285,6 +285,35 @@ __device__ __noinline__ int decompress_dense_v5(const uint8_t *__restrict__ in, 
     return SNP_OK;
 }
 
+// One block through the sparse prefix engine and, if the tags turn dense, the dense engine.
+__device__ __forceinline__ int decompress_block_v5(const uint8_t *in, uint32_t n_in, uint8_t *out, uint32_t cap,
+                                                   uint32_t *written, const uint32_t *lut, WarpQueue3 *q) {
+    uint32_t w = 0;
+    int st;
+    if (n_in >= 0x7fff0000u) {  // stream offsets are 32-bit with headroom here; v1 is safe to 2^32-1
+        st = decompress_block_v1(in, n_in, out, cap, &w);
+    } else {
+        uint32_t U, used;
+        st = varint_read(in, n_in, &U, &used);  // SnappyDecompressor.cs:50-63
+        if (st == SNP_OK && U > 0x7fffffffu) st = SNP_INVALID_LENGTH;
+        if (st == SNP_OK && cap < U) st = SNP_OUTPUT_TOO_SMALL;
+        if (st == SNP_OK && U != 0) {
+            const SparseResult r = sparse_run_v5(in, n_in, out, U, lut, used, 0);
+            if (r.status != SNP_OK) {
+                st = r.status;
+            } else if (r.done) {
+                st = r.op < U ? SNP_INCOMPLETE : SNP_OK;  // Snappy.cs:178-181
+                w = st == SNP_OK ? r.op : 0;
+            } else {
+                st = decompress_dense_v5(in, n_in, out, U, r.ip, r.op, &w, lut, q);
+            }
+        }
+    }
+    *written = w;
+    return st;
+}
+
+#ifndef SNP_EMU
 __global__ void __launch_bounds__(256, SNP_V3_CTAS)
 k_decompress_v5(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
                 const uint32_t *__restrict__ in_len, uint8_t *out_base,
@@ -302,30 +331,9 @@ k_decompress_v5(const uint8_t *__restrict__ in_base, const uint64_t *__restrict_
         if (lane == 0) item = atomicAdd(next_item, 1ull);
         item = __shfl_sync(SNP_FULL, item, 0);
         if (item >= n_items) break;
-        const uint8_t *in = in_base + in_off[item];
-        const uint32_t n_in = in_len[item], cap = out_cap[item];
-        uint8_t *out = out_base + out_off[item];
         uint32_t w = 0;
-        int st;
-        if (n_in >= 0x7fff0000u) {  // stream offsets are 32-bit with headroom here; v1 is safe to 2^32-1
-            st = decompress_block_v1(in, n_in, out, cap, &w);
-        } else {
-            uint32_t U, used;
-            st = varint_read(in, n_in, &U, &used);  // SnappyDecompressor.cs:50-63
-            if (st == SNP_OK && U > 0x7fffffffu) st = SNP_INVALID_LENGTH;
-            if (st == SNP_OK && cap < U) st = SNP_OUTPUT_TOO_SMALL;
-            if (st == SNP_OK && U != 0) {
-                const SparseResult r = sparse_run_v5(in, n_in, out, U, lut, used, 0);
-                if (r.status != SNP_OK) {
-                    st = r.status;
-                } else if (r.done) {
-                    st = r.op < U ? SNP_INCOMPLETE : SNP_OK;  // Snappy.cs:178-181
-                    w = st == SNP_OK ? r.op : 0;
-                } else {
-                    st = decompress_dense_v5(in, n_in, out, U, r.ip, r.op, &w, lut, q);
-                }
-            }
-        }
+        const int st = decompress_block_v5(in_base + in_off[item], in_len[item], out_base + out_off[item], out_cap[item],
+                                           &w, lut, q);
         if (lane == 0) {
             out_len[item] = w;
             status[item] = st;
@@ -333,5 +341,6 @@ k_decompress_v5(const uint8_t *__restrict__ in_base, const uint64_t *__restrict_
         __syncwarp();
     }
 }
+#endif  // !SNP_EMU
 
 }  // namespace snp
