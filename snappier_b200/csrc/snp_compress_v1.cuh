@@ -163,6 +163,7 @@ __device__ __noinline__ void compress_fragment_v1(const uint8_t *__restrict__ in
     if (ip < n) emit_literal_v1(o, in + ip, n - ip, lane);  // :406-411
 }
 
+#ifndef SNP_EMU
 // One item = varint(in_len) ++ CompressFragment(item)   (in_len <= 65536), i.e.
 // Snappy.TryCompress of a single-fragment input (SnappyCompressor.cs:24-83).
 // frag_mode != 0: no varint header (fragment of a larger input).
@@ -206,5 +207,7 @@ k_compress_v1(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
         __syncwarp();
     }
 }
+
+#endif  // !SNP_EMU
 
 }  // namespace snp

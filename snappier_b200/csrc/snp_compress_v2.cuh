@@ -34,6 +34,7 @@ namespace snp {
 // (bits 0..19) | stride of probe k (bits 20..31).  Data-independent.
 __device__ uint32_t g_probe_sched[SNP_SCHED_LEN];
 
+#ifndef SNP_EMU
 __global__ void k_init_probe_sched() {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         uint32_t skip = 32, off = 0;
@@ -45,6 +46,7 @@ __global__ void k_init_probe_sched() {
         }
     }
 }
+#endif  // !SNP_EMU
 
 // SnappyCompressor.cs:562-688 -- bounded common prefix of in[s1..] and in[s2..n), 128 bytes per ballot.
 __device__ __forceinline__ uint32_t find_match_length_v2(const uint8_t *__restrict__ in, uint32_t s1, uint32_t s2,
@@ -167,6 +169,7 @@ __device__ __noinline__ void compress_fragment_v2(const uint8_t *__restrict__ in
     if (next_emit < n) emit_literal_v1(o, in + next_emit, n - next_emit, lane);  // :406-411
 }
 
+#ifndef SNP_EMU
 template <int HASH_MODE>
 __global__ void __launch_bounds__(6 * SNP_WARP, 1)
 k_compress_v2(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
@@ -213,6 +216,8 @@ k_compress_v2(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
         __syncwarp();
     }
 }
+
+#endif  // !SNP_EMU
 
 // ---- k_compress_v3: same algorithm, hash tables in global memory (L2) ------------------------
 // One slice per resident warp, so the grid runs at full occupancy (the shared-memory kernel is
@@ -466,6 +471,7 @@ __device__ __noinline__ void compress_fragment_v4(const uint8_t *__restrict__ in
     if (next_emit < n) emit_literal_v1(o, in + next_emit, n - next_emit, lane);  // :406-411
 }
 
+#ifndef SNP_EMU
 template <int HASH_MODE, int VARIANT = 3>
 __global__ void __launch_bounds__(256)
 k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
@@ -517,5 +523,7 @@ k_compress_v3(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ 
         __syncwarp();
     }
 }
+
+#endif  // !SNP_EMU
 
 }  // namespace snp

@@ -251,3 +251,15 @@ static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long 
     return old;
 }
 static inline uint32_t __ldg(const uint32_t *p) { return *p; }
+template <class T>
+static inline T __ldcg(const T *p) { return *p; }
+template <class T>
+static inline void __stcg(T *p, T v) { *p = v; }
+static inline unsigned __match_any_sync(unsigned m, uint32_t v) {
+    SIMT_FULLMASK(m);
+    uint64_t all[32];
+    simt::gather(v, all, "match_any");
+    unsigned r = 0;
+    for (int l = 0; l < 32; l++) r |= (unsigned)((uint32_t)all[l] == v) << l;
+    return r;
+}
