@@ -29,6 +29,7 @@ __device__ __forceinline__ uint32_t crc_advance_bits(uint32_t r, int bits) {
     return r;
 }
 
+#ifndef SNP_EMU
 __global__ void k_init_crc_tables() {
     // T4[k][b]: register after absorbing a word whose byte k is b (others 0) = byte b advanced by 8*(4-k) bits.
     // T128[k][b]: the same advanced by another 124 bytes.
@@ -39,6 +40,7 @@ __global__ void k_init_crc_tables() {
         g_crc_tab[1024 + i] = crc_advance_bits(t4, 8 * 124);
     }
 }
+#endif  // !SNP_EMU
 
 // (a * b) mod P over GF(2), reflected bit order (bit 31 = x^0 ... as in zlib's multmodp)
 __device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {
@@ -67,6 +69,36 @@ __device__ __forceinline__ uint32_t crc_f(const uint32_t *tab, uint32_t y) {
     return tab[y & 0xff] ^ tab[256 + ((y >> 8) & 0xff)] ^ tab[512 + ((y >> 16) & 0xff)] ^ tab[768 + (y >> 24)];
 }
 
+// Crc32C(data) computed by one warp (tab = the 2048-entry table set above, usually in shared memory).
+__device__ __forceinline__ uint32_t crc32c_warp(const uint32_t *tab, const uint8_t *p, uint32_t n) {
+    const unsigned lane = lane_id();
+    // serial prefix up to 4-byte alignment (lane 0's register carries the ~0 init)
+    uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)p & 3)) & 3));
+    uint32_t state = 0xffffffffu;  // Crc32CAlgorithm.Append: crcLocal = uint.MaxValue ^ crc
+    // byte-wise step = table of a byte advanced 8 bits = T4[3]
+    for (uint32_t i = 0; i < head; i++) state = tab[768 + ((state ^ p[i]) & 0xff)] ^ (state >> 8);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p + head);
+    const uint32_t words = (n - head) >> 2;
+    const uint32_t steps = words >> 5;  // full 128-byte steps
+    uint32_t s = lane == 0 ? state : 0u;
+    if (steps) {
+        for (uint32_t j = 0; j + 1 < steps; j++) s = crc_f(tab + 1024, s ^ w[j * 32 + lane]);
+        s = crc_f(tab, s ^ w[(steps - 1) * 32 + lane]);
+        // align lane `lane` to the end of the region: 4*(31-lane) more bytes
+        s = crc_mulmod(crc_xpow8n(4 * (31 - lane)), s);
+        for (int d = 16; d; d >>= 1) s ^= __shfl_xor_sync(SNP_FULL, s, d);
+        state = s;
+    }
+    // serial tail: remaining words + bytes (warp-uniform work, < 128 + 3 bytes)
+    for (uint32_t j = steps * 32; j < words; j++) state = crc_f(tab, state ^ w[j]);
+    for (uint32_t i = head + words * 4; i < n; i++) state = tab[768 + ((state ^ p[i]) & 0xff)] ^ (state >> 8);
+    return ~state;
+}
+
+// Crc32CAlgorithm.ApplyMask, Crc32CAlgorithm.cs:157-158
+__device__ __forceinline__ uint32_t crc32c_mask(uint32_t crc) { return ((crc >> 15) | (crc << 17)) + 0xa282ead8u; }
+
+#ifndef SNP_EMU
 // One warp per item.  crc_out[i] = ApplyMask(Crc32C(data_i)).
 __global__ void __launch_bounds__(256)
 k_crc32c_masked_batch(const uint8_t *__restrict__ base, const uint64_t *__restrict__ off,
@@ -78,30 +110,8 @@ k_crc32c_masked_batch(const uint8_t *__restrict__ base, const uint64_t *__restri
     const size_t warps = (size_t)gridDim.x * (blockDim.x / SNP_WARP);
     for (size_t item = (size_t)blockIdx.x * (blockDim.x / SNP_WARP) + threadIdx.x / SNP_WARP; item < n_items;
          item += warps) {
-        const uint8_t *p = base + off[item];
-        const uint32_t n = len[item];
-        // serial prefix up to 4-byte alignment (lane 0's register carries the ~0 init)
-        uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)p & 3)) & 3));
-        uint32_t state = 0xffffffffu;  // Crc32CAlgorithm.Append: crcLocal = uint.MaxValue ^ crc
-        // byte-wise step = table of a byte advanced 8 bits = T4[3]
-        for (uint32_t i = 0; i < head; i++) state = tab[768 + ((state ^ p[i]) & 0xff)] ^ (state >> 8);
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(p + head);
-        const uint32_t words = (n - head) >> 2;
-        const uint32_t steps = words >> 5;  // full 128-byte steps
-        uint32_t s = lane == 0 ? state : 0u;
-        if (steps) {
-            for (uint32_t j = 0; j + 1 < steps; j++) s = crc_f(tab + 1024, s ^ w[j * 32 + lane]);
-            s = crc_f(tab, s ^ w[(steps - 1) * 32 + lane]);
-            // align lane `lane` to the end of the region: 4*(31-lane) more bytes
-            s = crc_mulmod(crc_xpow8n(4 * (31 - lane)), s);
-            for (int d = 16; d; d >>= 1) s ^= __shfl_xor_sync(SNP_FULL, s, d);
-            state = s;
-        }
-        // serial tail: remaining words + bytes (warp-uniform work, < 128 + 3 bytes)
-        for (uint32_t j = steps * 32; j < words; j++) state = crc_f(tab, state ^ w[j]);
-        for (uint32_t i = head + words * 4; i < n; i++) state = tab[768 + ((state ^ p[i]) & 0xff)] ^ (state >> 8);
-        uint32_t crc = ~state;
-        if (masked) crc = ((crc >> 15) | (crc << 17)) + 0xa282ead8u;  // Crc32CAlgorithm.ApplyMask, :157-158
+        uint32_t crc = crc32c_warp(tab, base + off[item], len[item]);
+        if (masked) crc = crc32c_mask(crc);
         if (lane == 0) crc_out[item] = crc;
     }
 }
@@ -141,5 +151,7 @@ __global__ void k_frame_emit(const uint8_t *__restrict__ raw, const uint64_t *__
         for (uint32_t k = threadIdx.x; k < payload; k += blockDim.x) d[8 + k] = src[k];
     }
 }
+
+#endif  // !SNP_EMU
 
 }  // namespace snp

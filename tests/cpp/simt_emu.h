@@ -179,6 +179,11 @@ static inline T __shfl_down_sync(unsigned m, T v, unsigned d) {
     const unsigned l = simt::lane();
     return simt::exchange<T>(v, l + d < 32 ? l + d : l, "shfl_down");
 }
+template <class T>
+static inline T __shfl_xor_sync(unsigned m, T v, unsigned x) {
+    SIMT_FULLMASK(m);
+    return simt::exchange<T>(v, (unsigned)simt::lane() ^ x, "shfl_xor");
+}
 static inline unsigned __ballot_sync(unsigned m, bool p) {
     SIMT_FULLMASK(m);
     uint64_t all[32];
