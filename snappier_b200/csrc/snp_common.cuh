@@ -19,12 +19,12 @@ __device__ __forceinline__ unsigned lanemask_lt() { return (1u << simt::lane()) 
 #else
 __device__ __forceinline__ unsigned lane_id() {
     unsigned l;
-    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    asm("mov.u32 %0, %%laneid;" : "=r"(l));  // not volatile: constant per thread, the compiler may hoist / reuse it
     return l;
 }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
-    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
 #endif

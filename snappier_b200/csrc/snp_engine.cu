@@ -21,11 +21,9 @@
 #include "snp_compress_v2.cuh"
 #include "snp_compress_v5.cuh"
 #include "snp_decompress_v1.cuh"
-#include "snp_decompress_v2.cuh"
 #include "snp_decompress_v3.cuh"
-#include "snp_decompress_v4.cuh"
 #include "snp_decompress_v5.cuh"
-#include "snp_decompress_v6.cuh"
+#include "snp_decompress_v7.cuh"
 #include "snp_frame.cuh"
 
 namespace {
@@ -100,18 +98,10 @@ struct snp_ctx {
     std::mutex mu;
     std::atomic<uint64_t> launches{0};
     int sm_count = 148;
-    int decomp_kernel = 5;  // SNP_DECOMP_KERNEL (1 = baseline, 2/3 = warp-parallel, 5 = 3 + sparse-tag prefix engine: the
-                            // default; 4 = 3 + TMA-staged input, measured 10 % slower than 3 because the kernel is
-                            // issue-bound; 6 = checkpointed two-pass, tag-per-lane decode for batches
-                            // of >= v6_min_items blocks (smaller ones take 5): 1.65x faster than 5 on long-tag data,
-                            // slower on dense-tag data)
-    int v6_min_items = 256;     // SNP_V6_MIN_ITEMS: below this the per-thread tag scan cannot fill the GPU
-    size_t v6_wave = 262144;    // SNP_V6_WAVE: blocks per scan/decode kernel pair (bounds the checkpoint scratch: 6 KB per
-                                // block; the thread-per-block scan needs >= 189 k blocks in flight to fill the GPU)
-    DevBuf d_v6;                // checkpoint scratch of device-mode / single-call launches
-    cudaEvent_t v6_done = nullptr;  // orders users of d_v6 that arrive on different streams
-    cudaStream_t v6_last_stream = nullptr;
-    bool v6_used = false;
+    int decomp_kernel = 7;  // SNP_DECOMP_KERNEL: 7 = tag-group engine (TMA-staged input ring, advance-table walk, output
+                            // window; the default), 5 = the round-1 default (sparse-tag prefix engine + speculative
+                            // dense engine; kept as the A/B challenger), 1 = warp-uniform baseline
+    int v7_window = 2048;   // SNP_V7_WINDOW: output window bytes per warp of k_decompress_v7 (2048: 48 warps per SM, 4096: 32)
     int comp_kernel = 3;    // SNP_COMP_KERNEL (1 = baseline, 2 = smem tables, 3 = L2 tables, 4 = 3 + register window,
                             // 5 = two blocks per warp (half-warps): measured 10-15 % slower than 3, DESIGN.md 4.6;
                             // 4 measured equal to 3: the kernel is bound by random table sectors)
@@ -133,7 +123,7 @@ struct snp_ctx {
     struct Slot {
         cudaStream_t stream = nullptr;
         cudaEvent_t meta_ready = nullptr;
-        DevBuf d_in, d_out, d_meta, d_v6;
+        DevBuf d_in, d_out, d_meta;
         PinnedBuf h_meta;  // same layout as d_meta: async both ways regardless of the caller's arrays
     } slots[kSlots];
     bool attrs_set = false;
@@ -161,8 +151,10 @@ int ctx_set_attrs(snp_ctx *c) {
                             (int)kComp2Smem));
     CU(cudaFuncSetAttribute(snp::k_compress_v2<SNP_HASH_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kComp2Smem));
-    CU(cudaFuncSetAttribute(snp::k_decode_v6, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(snp::V6DecSmem)));
+    CU(cudaFuncSetAttribute(snp::k_decompress_v7<2048, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(8 * sizeof(snp::Warp7<2048>))));
+    CU(cudaFuncSetAttribute(snp::k_decompress_v7<4096, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(8 * sizeof(snp::Warp7<4096>))));
 
     c->attrs_set = true;
     return SNP_OK;
@@ -189,84 +181,38 @@ int env_int(const char *name, int dflt) {
 
 // ---------------------------------------------------------------- launches --
 
-// v6: per wave of <= v6_wave blocks, k_tagscan_v6 (thread per block: status + checkpoints) then
-// k_decode_v6 (warp per block).  `scratch` = the calling pipeline slot's buffer, or nullptr for the
-// context's own (then launches arriving on different streams are ordered with an event).
-int launch_decompress_v6(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const uint64_t *in_off,
-                         const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off,
-                         const uint32_t *out_cap, uint32_t *out_len, int32_t *status, size_t n, DevBuf *scratch) {
-    int rc = ctx_set_attrs(c);
-    if (rc) return rc;
-    const bool own = scratch == nullptr;
-    if (own) {
-        scratch = &c->d_v6;
-        if (!c->v6_done) CU(cudaEventCreateWithFlags(&c->v6_done, cudaEventDisableTiming));
-        if (c->v6_used && c->v6_last_stream != s) CU(cudaStreamWaitEvent(s, c->v6_done, 0));
-    }
-    const size_t wave = std::min(n, c->v6_wave);
-    const size_t nt_bytes = align_up(wave * 4, 256);
-    if ((rc = scratch->reserve(nt_bytes + wave * (size_t)SNP6_CKB * sizeof(uint2)))) return rc;
-    uint32_t *ntags = (uint32_t *)scratch->p;
-    uint2 *ck = (uint2 *)((uint8_t *)scratch->p + nt_bytes);
-    for (size_t a0 = 0; a0 < n; a0 += wave) {
-        const size_t nw = std::min(wave, n - a0);
-        unsigned long long *ctr_a, *ctr_b;
-        if ((rc = ctx_work_counter(c, s, &ctr_a))) return rc;
-        if ((rc = ctx_work_counter(c, s, &ctr_b))) return rc;
-        snp::Scan6Args sa{in_base, in_off, in_len, out_cap, out_len, status, a0, nw, ctr_a, ntags, ck};
-        const size_t scan_ctas = (nw + SNP6_SCAN_WARPS * 32 - 1) / (SNP6_SCAN_WARPS * 32);
-        const unsigned gs = (unsigned)std::min(scan_ctas, (size_t)c->sm_count * SNP6_SCAN_CTAS);
-        snp::k_tagscan_v6<<<gs, SNP6_SCAN_WARPS * 32, 0, s>>>(sa);
-        snp::Decode6Args da{in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, a0, nw, ctr_b, ntags, ck};
-        const size_t dec_ctas = (nw + SNP6_DEC_WARPS - 1) / SNP6_DEC_WARPS;
-        const unsigned gd = (unsigned)std::min(dec_ctas, (size_t)c->sm_count * SNP6_DEC_CTAS);
-        snp::k_decode_v6<<<gd, SNP6_DEC_WARPS * 32, sizeof(snp::V6DecSmem), s>>>(da);
-        c->launches += 2;
-        CU(cudaGetLastError());
-    }
-    if (own) {
-        CU(cudaEventRecord(c->v6_done, s));
-        c->v6_last_stream = s;
-        c->v6_used = true;
-    }
-    return SNP_OK;
-}
-
 int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const uint64_t *in_off,
                       const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off,
-                      const uint32_t *out_cap, uint32_t *out_len, int32_t *status, size_t n,
-                      DevBuf *v6_scratch = nullptr) {
+                      const uint32_t *out_cap, uint32_t *out_len, int32_t *status, size_t n) {
     if (n == 0) return SNP_OK;
-    int kernel = c->decomp_kernel;
-    if (kernel == 6) {
-        if (n >= (size_t)c->v6_min_items)
-            return launch_decompress_v6(c, s, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n,
-                                        v6_scratch);
-        kernel = 5;
-    }
+    const int kernel = c->decomp_kernel;
     const int warps = 8;
     unsigned grid = (unsigned)((n + warps - 1) / warps);
-    if (kernel == 1)
+    if (kernel == 7) {
+        int rc = ctx_set_attrs(c);
+        if (rc) return rc;
+        unsigned long long *ctr;
+        if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
+        if (c->v7_window == 4096) {
+            const unsigned pgrid = std::min(grid, (unsigned)(c->sm_count * 4));
+            snp::k_decompress_v7<4096, 4><<<pgrid, warps * SNP_WARP, 8 * sizeof(snp::Warp7<4096>), s>>>(
+                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, ctr);
+        } else {
+            const unsigned pgrid = std::min(grid, (unsigned)(c->sm_count * 6));
+            snp::k_decompress_v7<2048, 6><<<pgrid, warps * SNP_WARP, 8 * sizeof(snp::Warp7<2048>), s>>>(
+                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, ctr);
+        }
+    } else if (kernel == 1)
         snp::k_decompress_v1<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
-                                                               out_cap, out_len, status, n);
-    else if (kernel == 2)
-        snp::k_decompress_v2<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
                                                                out_cap, out_len, status, n);
     else {
         unsigned long long *ctr;
         int rc = ctx_work_counter(c, s, &ctr);
         if (rc) return rc;
-        unsigned pgrid = (unsigned)(c->sm_count * (kernel == 4 ? 6 : SNP_V3_CTAS));
+        unsigned pgrid = (unsigned)(c->sm_count * SNP_V3_CTAS);
         if (pgrid > grid) pgrid = grid;
-        if (kernel == 3)
-            snp::k_decompress_v3<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
-                                                                    out_cap, out_len, status, n, ctr);
-        else if (kernel == 5)
-            snp::k_decompress_v5<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
-                                                                    out_cap, out_len, status, n, ctr);
-        else
-            snp::k_decompress_v4<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
-                                                                    out_cap, out_len, status, n, ctr);
+        snp::k_decompress_v5<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
+                                                                out_cap, out_len, status, n, ctr);
     }
     c->launches++;
     CU(cudaGetLastError());
@@ -485,7 +431,7 @@ int chunk_phase1(snp_ctx *c, Chunk &ck, bool compress, const uint8_t *in_base, c
                              d_out_cap, d_out_len, d_status, n, hash_mode, 0);
     else
         rc = launch_decompress(c, s, (const uint8_t *)sl.d_in.p, d_in_off, d_in_len, (uint8_t *)sl.d_out.p,
-                               d_out_off, d_out_cap, d_out_len, d_status, n, &sl.d_v6);
+                               d_out_off, d_out_cap, d_out_len, d_status, n);
     if (rc) return rc;
     if (c->host_trace) CU(cudaEventRecord(tev[2], s));
     // out_len + status are contiguous: one D2H into the pinned mirror (copied to the caller in phase 2)
@@ -812,9 +758,8 @@ int snp_create(int device, snp_ctx **out) {
     snp::k_init_probe_sched<<<1, 32, 0, c->stream>>>();
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 5);
-    c->v6_min_items = std::max(1, env_int("SNP_V6_MIN_ITEMS", 256));
-    c->v6_wave = (size_t)std::max(1, env_int("SNP_V6_WAVE", 262144));
+    c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 7);
+    c->v7_window = env_int("SNP_V7_WINDOW", 2048);
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));
@@ -833,7 +778,6 @@ void snp_destroy(snp_ctx *c) {
         cudaStreamDestroy(c->stream);
     }
     if (c->d_counters) cudaFree(c->d_counters);
-    if (c->v6_done) cudaEventDestroy(c->v6_done);
     if (c->tables_done) cudaEventDestroy(c->tables_done);
     for (auto &sl : c->slots) {
         if (sl.stream) cudaStreamSynchronize(sl.stream), cudaStreamDestroy(sl.stream);

@@ -7,6 +7,8 @@ import os
 import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "build")  # host emulator binaries (git-ignored)
 CORPUS = ["alice29.txt", "asyoulik.txt", "fireworks.jpeg", "geo.protodata", "html", "html_x_4",
           "kppkn.gtb", "lcet10.txt", "paper-100k.pdf", "plrabn12.txt", "urls.10K"]
 
@@ -102,3 +104,80 @@ def synthetic_blocks(seed: int, count: int, size: int = 65536) -> list[bytes]:
             b = (pat * (size // per + 1))[:size]
         res.append(b)
     return res
+
+
+def handmade_tag_forms() -> list[bytes]:
+    """Hand-assembled blocks: COPY4, multi-byte literal lengths, literals around the 64 / 128-byte path boundaries,
+    offsets around 16, literals > 64 bytes at every slot position, chained near / far copies."""
+    rng = np.random.default_rng(12)
+    lit = rng.integers(0, 256, size=70000, dtype=np.uint8).tobytes()
+
+    def varint(v):
+        out = bytearray()
+        while v >= 0x80:
+            out.append((v & 0x7f) | 0x80)
+            v >>= 7
+        out.append(v)
+        return bytes(out)
+
+    def literal(data):
+        n = len(data) - 1
+        if n < 60:
+            return bytes([n << 2]) + data
+        k = (n.bit_length() + 7) // 8
+        return bytes([(59 + k) << 2]) + n.to_bytes(k, "little") + data
+
+    def copy(off, ln):
+        return bytes([((ln - 1) << 2) | 2]) + off.to_bytes(2, "little")
+
+    items = []
+    body = bytes([62 << 2]) + (len(lit) - 1).to_bytes(3, "little") + lit
+    body += bytes([((10 - 1) << 2) | 3]) + (69000).to_bytes(4, "little")
+    body += bytes([((64 - 1) << 2) | 3]) + (3).to_bytes(4, "little")
+    items.append(varint(70000 + 10 + 64) + body)
+    items.append(varint(70000) + bytes([63 << 2]) + (len(lit) - 1).to_bytes(4, "little") + lit)
+    items.append(varint(300) + bytes([61 << 2]) + (299).to_bytes(2, "little") + lit[:300])
+    items.append(varint(20) + bytes([3 << 2]) + b"abcd" + bytes([(4 - 1) << 2 | 3]) + (0).to_bytes(4, "little"))
+    items.append(varint(20) + bytes([3 << 2]) + b"abcd" + bytes([(4 - 1) << 2 | 3]) + (5).to_bytes(4, "little"))
+    # every copy offset 1..40 x lengths around the 16-byte trips, each after literals of boundary sizes
+    for lit_len in (1, 15, 16, 17, 63, 64, 65, 127, 128, 129, 200, 1100, 3000):
+        body, total = bytearray(), 0
+        body += literal(lit[:lit_len])
+        total += lit_len
+        for off in list(range(1, 41)) + [63, 64, 65, 100]:
+            for ln in (1, 4, 15, 16, 17, 31, 32, 33, 48, 63, 64):
+                if off <= total:
+                    body += copy(off, ln)
+                    total += ln
+            body += literal(lit[total % 5000: total % 5000 + (off % 7) + 1])
+            total += (off % 7) + 1
+        items.append(varint(total) + bytes(body))
+    # a literal > 64 bytes at every slot position around the group boundary (head + length never split: pad slot),
+    # with lengths whose low byte looks like a literal head (0x80) or is zero
+    for pre in range(27, 36):
+        for big in (65, 128, 256, 0x180, 1000):
+            body, total = bytearray(), 0
+            for i in range(pre):
+                body += literal(lit[i:i + 1 + (i % 3)])
+                total += 1 + (i % 3)
+            body += literal(lit[100:100 + big])
+            total += big
+            for off, ln in ((1, 20), (big, 33), (5, 4), (total // 2, 64)):
+                body += copy(off, ln)
+                total += ln
+            body += literal(lit[7:7 + big + 3])
+            total += big + 3
+            items.append(varint(total) + bytes(body))
+    # long runs of chained far/near copies and literals > 64 interleaved (window slide + re-seed)
+    body, total = bytearray(), 0
+    for i in range(400):
+        n = int(rng.integers(1, 300))
+        body += literal(lit[i * 100: i * 100 + n])
+        total += n
+        for _ in range(int(rng.integers(0, 6))):
+            off = int(rng.integers(1, min(total, 65535) + 1))
+            ln = int(rng.integers(1, 65))
+            body += copy(off, ln)
+            total += ln
+    items.append(varint(total) + bytes(body))
+    return items

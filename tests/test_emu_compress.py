@@ -11,7 +11,7 @@ import subprocess
 import pytest
 
 from tests import helpers as H
-from tests.test_emu_v6 import BUILD, ROOT
+from tests.helpers import BUILD, ROOT
 
 
 @pytest.fixture(scope="module")

@@ -8,7 +8,7 @@ import subprocess
 
 import numpy as np
 
-from tests.test_emu_v6 import BUILD, ROOT
+from tests.helpers import BUILD, ROOT
 
 
 def test_emu_crc32c_warp(oracle, tmp_path):

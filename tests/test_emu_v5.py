@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from tests import helpers as H
-from tests.test_emu_v6 import BUILD, ROOT, handmade_tag_forms
+from tests.helpers import BUILD, ROOT, handmade_tag_forms
 
 
 @pytest.fixture(scope="module")

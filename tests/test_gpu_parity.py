@@ -337,17 +337,18 @@ def test_device_mode_large_batch_properties(engine, oracle):
     ch = comp.view(n, pitch)
     for i in (0, 1, 63, 64, 2047, 4095):
         assert ch[i, : cl[i]].cpu().numpy().tobytes() == oracle.compress(blocks[i % len(blocks)])[1]
-    # the two-pass kernel (SNP_DECOMP_KERNEL=6) on the same device-resident batch, in three waves
-    e6 = _engine_with({"SNP_DECOMP_KERNEL": "6", "SNP_V6_WAVE": "1500"})
-    out.zero_()
-    o_len.zero_()
-    status2.fill_(-99)
-    e6.decompress_batch_device(comp, c_off, c_len, out, o_off, o_cap, o_len, status2, stream)
-    torch.cuda.synchronize()
-    assert e6.launch_count == 6  # 3 waves x (tag scan + decode)
-    assert int(status2.abs().sum()) == 0 and bool((o_len == 65536).all())
-    assert torch.equal(out.view(n // len(blocks), -1), src.view(1, -1).expand(n // len(blocks), -1))
-    e6.close()
+    # the 4 KiB-window instantiation of the default kernel and the round-1 kernel on the same device-resident batch
+    for env in ({"SNP_V7_WINDOW": "4096"}, {"SNP_DECOMP_KERNEL": "5"}):
+        ex = _engine_with(env)
+        out.zero_()
+        o_len.zero_()
+        status2.fill_(-99)
+        ex.decompress_batch_device(comp, c_off, c_len, out, o_off, o_cap, o_len, status2, stream)
+        torch.cuda.synchronize()
+        assert ex.launch_count == 1
+        assert int(status2.abs().sum()) == 0 and bool((o_len == 65536).all())
+        assert torch.equal(out.view(n // len(blocks), -1), src.view(1, -1).expand(n // len(blocks), -1))
+        ex.close()
 
 
 def _engine_with(env: dict):
@@ -370,11 +371,9 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     and statuses on corpus blocks, synthetic blocks and corrupted blocks."""
     from snappier_b200.batch import compress_many, decompress_many
     e1 = _engine_with({"SNP_DECOMP_KERNEL": "1", "SNP_COMP_KERNEL": "1"})
-    e2 = _engine_with({})
-    e4 = _engine_with({"SNP_DECOMP_KERNEL": "4"})  # TMA-staged input ring
-    e5 = _engine_with({"SNP_DECOMP_KERNEL": "5"})  # sparse-tag prefix engine + dense engine
-    e3 = _engine_with({"SNP_DECOMP_KERNEL": "3"})
-    e6 = _engine_with({"SNP_DECOMP_KERNEL": "6", "SNP_V6_MIN_ITEMS": "1"})  # two-pass, tag-per-lane (forced for tiny batches too)
+    e2 = _engine_with({})                            # default: tag-group engine, 2 KiB output window
+    e4 = _engine_with({"SNP_V7_WINDOW": "4096"})     # the same engine with a 4 KiB window (32 warps per SM)
+    e5 = _engine_with({"SNP_DECOMP_KERNEL": "5"})    # round-1 default: sparse-tag prefix engine + speculative dense engine
     _, blocks = _corpus_blocks(fixtures)
     blocks = blocks + H.synthetic_blocks(5150, 48)
     c1, s1 = compress_many(e1, blocks, 0)
@@ -399,7 +398,7 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     assert d2[:len(blocks)] == blocks
     d4, s4 = decompress_many(e4, items, caps)
     assert np.array_equal(s4, s2) and d4 == d2
-    for ex in (e3, e5, e6):
+    for ex in (e5,):
         dx, sx = decompress_many(ex, items, caps)
         assert np.array_equal(sx, s1) and dx == d1
     # ragged / tiny / unaligned inputs through the ring's head-tail byte path
@@ -407,32 +406,27 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     d4s, s4s = decompress_many(e4, small)
     d2s, s2s = decompress_many(e2, small)
     assert d4s == d2s and not s4s.any()
-    d6s, s6s = decompress_many(e6, small)
-    assert d6s == d2s and not s6s.any()
-    # long literals at every source/destination alignment (the vectorised literal path of kernel 5)
+    assert d2s == [oracle.decompress(c)[1] for c in small] and not s2s.any()
+    # long literals at every source/destination alignment (the vectorised literal paths)
     rng2 = np.random.default_rng(23)
     lits = []
     for n in (127, 128, 129, 143, 144, 145, 300, 1000, 4097, 70001):
         for pad in (0, 1, 5, 15):
             raw = rng2.integers(0, 256, size=n + pad, dtype=np.uint8).tobytes()
             lits.append(oracle.compress(raw)[1])  # incompressible -> (pad-shifted) long literals
-    for ex in (e1, e3, e5, e6):
+    for ex in (e1, e2, e4, e5):
         dl, sl = decompress_many(ex, lits)
         assert not sl.any() and dl == [oracle.decompress(c)[1] for c in lits]
-    e1.close()
-    e2.close()
-    e3.close()
-    e4.close()
-    e5.close()
-    e6.close()
+    for ex in (e1, e2, e4, e5):
+        ex.close()
 
 
-def test_v6_waves_work_stealing_and_fallback(oracle, fixtures):
-    """Kernel 6 with tiny waves (many scan/decode kernel pairs), thousands of ragged blocks sharing
-    16-byte output vectors with their neighbours, and blocks denser than the checkpoint budget
-    (handed to the v3 engine inside the decode kernel)."""
+@pytest.mark.parametrize("env", [{}, {"SNP_V7_WINDOW": "4096"}])
+def test_ragged_blocks_work_stealing_and_dense_tags(oracle, fixtures, env):
+    """The default kernel on thousands of ragged blocks that share 16-byte output vectors with their neighbours (the
+    window flush must not touch a neighbour's bytes) and on a block of > 24 576 tiny tags."""
     from snappier_b200.batch import decompress_many
-    e6 = _engine_with({"SNP_DECOMP_KERNEL": "6", "SNP_V6_MIN_ITEMS": "1", "SNP_V6_WAVE": "700"})
+    e6 = _engine_with(env)
     _, blocks = _corpus_blocks(fixtures)
     blocks = blocks + H.synthetic_blocks(808, 60)
     rng = np.random.default_rng(5)
@@ -457,13 +451,14 @@ def test_v6_waves_work_stealing_and_fallback(oracle, fixtures):
     e6.close()
 
 
-def test_v6_handmade_tag_forms_and_fuzz(oracle):
-    """Kernel 6 on the hand-assembled tag forms the emulator tests use (COPY4, literal-length forms, literals > 64
-    bytes at every slot position, every offset 1..40 x lengths around the 16-byte trips) and on mutated blocks:
-    status and bytes equal the oracle's."""
+@pytest.mark.parametrize("env", [{}, {"SNP_V7_WINDOW": "4096"}])
+def test_handmade_tag_forms_and_fuzz(oracle, env):
+    """The default kernel on the hand-assembled tag forms the emulator tests use (COPY4, literal-length forms, literals
+    > 64 bytes at every position of a tag group, every offset 1..40 x lengths around 16 / 32 / 64) and on mutated
+    blocks: status and bytes equal the oracle's."""
     from snappier_b200.batch import decompress_many
-    from tests.test_emu_v6 import handmade_tag_forms
-    e6 = _engine_with({"SNP_DECOMP_KERNEL": "6", "SNP_V6_MIN_ITEMS": "1"})
+    from tests.helpers import handmade_tag_forms
+    e6 = _engine_with(env)
     items = handmade_tag_forms()
     rng = np.random.default_rng(4)
     for b in list(items[5:40]):

@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
 """Per-data-class decompress throughput of selected kernel variants (diagnostics, not the headline bench).
 
-    python tools/class_bench.py [--blocks 32768] [--variants 5,6] [--out gpurun_out/class_bench.json]
+    python tools/class_bench.py [--blocks 32768] [--variants 7,7w4096,5] [--out gpurun_out/class_bench.json]
 
 Classes are bench.py's 'Silesia-mix synthetic' components, one class per batch; every timed output is
-verified against the raw blocks' checksums.  Also sweeps small mixed batches to place the v5/v6 crossover.
+verified against the raw blocks' checksums.  Also times small mixed batches (launch-latency regime).
 """
 from __future__ import annotations
 
@@ -73,7 +73,7 @@ def time_decompress(torch, engine, comp, c_off, c_len, sums, weights, n, dev, re
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blocks", type=int, default=1 << 15)
-    ap.add_argument("--variants", default="5,6")
+    ap.add_argument("--variants", default="7,7w4096,5")
     ap.add_argument("--small", default="64,256,1024,4096")
     ap.add_argument("--classes", default="", help="comma-separated subset of class names (default: all)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "class_bench.json"))
@@ -82,9 +82,9 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     variants = args.variants.split(",")
-    def env_of(v):  # "5" or "5p3" = kernel 5 with SNP_V5_PREFETCH=3
-        k, _, pf = v.partition("p")
-        return {"SNP_DECOMP_KERNEL": k, "SNP_V6_MIN_ITEMS": "1", "SNP_V6_WAVE": os.environ.get("SNP_V6_WAVE", "262144")}
+    def env_of(v):  # "7" = default kernel, "7w4096" = its 4 KiB-window instantiation, "5" = the round-1 kernel
+        k, _, w = v.partition("w")
+        return {"SNP_DECOMP_KERNEL": k, "SNP_V7_WINDOW": w or "2048"}
     engines = {v: engine_with(env_of(v)) for v in variants}
     prep_engine = engines[variants[0]]
     res = {"blocks": args.blocks, "classes": {}, "small_mix": {}}
