@@ -52,12 +52,16 @@ namespace snp {
 #define SNP7_STAT(ng)  // tests/cpp/emu_v7.cpp counts fast-path tags per group with this hook
 #endif
 
+#define SNP7_MIRROR 64u    // ring[R, R+64) repeats ring[0, 64): a tag that starts in front of the lap end is read linearly
+#define SNP7_STAGE_W 5u    // words per lane of the far-source staging area (sources of <= 16 bytes at any alignment)
+
 template <uint32_t W>
 struct alignas(16) Warp7 {
-    uint8_t win[W];                   // output window: position x lives at (out address + x) mod W
-    uint8_t ring[SNP7_R + 16];        // compressed input: position p lives at (in address + p) mod R; [R, R+4) mirrors [0, 4)
-    uint8_t adv[SNP7_R + SNP7_PAD];   // advance table, same indexing as ring
-    uint32_t tagpos[32];              // ring index of tag k of the current group
+    uint8_t win[W];                      // output window: position x lives at (out address + x) mod W
+    uint8_t ring[SNP7_R + SNP7_MIRROR];  // compressed input: position p lives at (in address + p) mod R
+    uint8_t adv[SNP7_R + SNP7_PAD];      // advance table, same indexing as ring
+    uint32_t stage[32 * SNP7_STAGE_W];   // sources of this group's far back-references, fetched once per group
+    uint32_t tagpos[32];                 // shared-memory address of the advance byte of tag k of the current group
     uint64_t bar[SNP7_SLOTS];
 };
 
@@ -131,24 +135,29 @@ template <class S> __device__ __forceinline__ uint32_t sm_ld8(const S *, uint32_
 }
 #endif
 
-// Once per warp, before its first block: barriers, the zero pad of the advance table, and tag slots that point into the
-// advance table (lanes behind a short walk read whatever their slot held last).
+// Once per warp, before its first block: barriers; an all-zero advance table (the walk may run through entries of
+// chunks that have not landed: they must be advances a chunk once produced (<= 61) or 0, never uninitialised shared
+// memory, and the pad behind the table stays 0 for good); tag slots that point into the advance table (lanes behind a
+// short walk read whatever their slot held last).
 template <uint32_t W>
 __device__ __forceinline__ void warp7_init(Warp7<W> *s, unsigned lane) {
     if (lane < SNP7_SLOTS) mbar_init(&s->bar[lane], 1);
     s->tagpos[lane] = sm_off(s, s->adv);
-    s->adv[SNP7_R + lane] = 0;
-    s->adv[SNP7_R + 32 + lane] = 0;
+    for (uint32_t k = lane; k < (SNP7_R + SNP7_PAD) / 4; k += SNP_WARP) reinterpret_cast<uint32_t *>(s->adv)[k] = 0;
 }
 
 template <uint32_t W>
 __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, uint32_t n_in, uint8_t *out,
                                                 uint32_t cap, uint32_t *written, Warp7<W> *s, uint32_t &phases) {
     constexpr uint32_t R = SNP7_R, CH = SNP7_CH;
-    constexpr uint32_t FLUSH_AT = W / 4;   // flush the window when this much is pending
-    constexpr uint32_t GMAX = W / 2;       // output bytes per tag group
-    constexpr uint32_t NEAR_MAX = W - 64;  // back-references up to this distance are served by the window
+    constexpr uint32_t FLUSH_AT = W / 4;                     // flush the window when this much is pending
+    constexpr uint32_t GMAX = W / 2 < 1024 ? W / 2 : 1024;   // output bytes per tag group (<= 32 rounds)
+    constexpr uint32_t NEAR_MAX = W - 64;                    // back-references up to this distance are served by the window
     static_assert((W & (W - 1)) == 0 && W >= 1024 && W <= 32768, "window size");
+    constexpr uint32_t RING_OFF = W;                         // byte offsets inside Warp7<W>; win sits at 0
+    constexpr uint32_t STAGE_OFF = W + 2 * SNP7_R + SNP7_MIRROR + SNP7_PAD;
+    // descriptor flags (see GROUP below)
+    constexpr uint32_t D_WIN = 0x80000000u, D_GLOBAL = 0x40000000u, D_CLOSE = 0x20000000u;
     const unsigned lane = lane_id();
     const unsigned le = (2u << lane) - 1u;  // lanes <= me
     *written = 0;
@@ -160,7 +169,7 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
     if (U == 0) return SNP_OK;
 
     // 16-byte-aligned views: stream byte p sits at aligned offset skew + p of in16 (ring index (skew + p) mod R),
-    // output byte x at aligned offset oskew + x of out16 (window index (oskew + x) mod W).
+    // output byte x at aligned offset ("window coordinate") oskew + x of out16 (window index (oskew + x) mod W).
     const uint32_t skew = (uint32_t)((uintptr_t)in & 15);
     const uint8_t *in16 = in - skew;
     const uint32_t A = skew + n_in;
@@ -168,7 +177,6 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
     const uint32_t oskew = (uint32_t)((uintptr_t)out & 15);
     uint8_t *out16 = out - oskew;
     uint8_t *sb = reinterpret_cast<uint8_t *>(s);
-    constexpr uint32_t RING_OFF = W;  // offsetof(Warp7<W>, ring); win sits at 0
 
     uint32_t issued = 0, ready = 0;  // chunks [ready, issued) are in flight
     uint32_t refill_at = 0, landed_end = 0;
@@ -189,6 +197,8 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
             }
         }
         *reinterpret_cast<uint2 *>(s->adv + ri) = make_uint2(a0, a1);
+        if ((c & (SNP7_SLOTS - 1)) == 0 && lane < SNP7_MIRROR / 4)  // a new lap begins: repeat its head behind the ring
+            reinterpret_cast<uint32_t *>(s->ring)[R / 4 + lane] = reinterpret_cast<const uint32_t *>(s->ring)[lane];
     };
     auto wait_chunk = [&](uint32_t c, bool compute) {
         const uint32_t slot = c & (SNP7_SLOTS - 1);
@@ -200,16 +210,21 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
         }
         (void)spins;
         phases ^= 1u << slot;
-        if (compute) {
-            chunk_adv(c);
-            if (slot == 0 && lane < 4) s->ring[R + lane] = s->ring[lane];  // tag bytes are read at i, i+1, i+2 without a wrap
-        }
+        if (compute) chunk_adv(c);
         __syncwarp();
     };
     auto issue_chunk = [&](uint32_t c) {
         const uint32_t slot = c & (SNP7_SLOTS - 1);
+        const uint32_t c0 = c * CH;
+        if (c != 0 && c0 + CH <= (A & ~15u)) {  // uniform: interior chunk = one 256-byte bulk copy
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&s->bar[slot], CH);
+                tma_load_1d(s->ring + slot * CH, in16 + c0, CH, &s->bar[slot]);
+            }
+            return;
+        }
         const uint32_t blo = (skew + 15u) & ~15u, bhi = A & ~15u;  // [blo, bhi) may be bulk-copied
-        const uint32_t c0 = c * CH, c1 = min(c0 + CH, (A + 15u) & ~15u);
+        const uint32_t c1 = min(c0 + CH, (A + 15u) & ~15u);
         const uint32_t b0 = max(c0, blo), b1 = min(c1, bhi);
         if (lane == 0) {
             if (b1 > b0) {
@@ -229,12 +244,12 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
     // drop the chunks below stream position pos, prefetch as far as the slots allow
     auto refill = [&](uint32_t pos) {
         const uint32_t keep = (skew + pos) / CH;  // oldest live chunk
-        __syncwarp();  // every lane is done reading the slots that are about to be overwritten
         if (keep > issued) {  // jumped over chunks that were never needed (long literal)
             while (ready < issued) wait_chunk(ready++, false);
             issued = ready = keep;
         }
         while (ready < keep && ready < issued) wait_chunk(ready++, false);  // a slot is re-armed only after its wait
+        __syncwarp();  // every lane is done reading the slots that are about to be overwritten
         while (issued < n_chunks && issued < keep + SNP7_SLOTS) issue_chunk(issued++);
         __syncwarp();
         refill_at = (keep + 1) * CH - skew;
@@ -335,14 +350,15 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
 
         // ---- WALK: shared-memory address of the advance byte of each of the next 32 tags (the walk stops advancing
         //      at anything the fast path cannot take: advance 0).  One load, one add, one store per tag.
-        const uint32_t i0 = (skew + ip) & (R - 1);
-        const uint32_t alim = adv0 + min(R, i0 + (landed_end - ip));
+        const uint32_t a_ip = adv0 + ((skew + ip) & (R - 1));   // address of ip's advance byte
+        const uint32_t a_land = a_ip + (landed_end - ip);       // address-space image of landed_end (may pass the lap end)
+        const uint32_t a_lim = min(a_land, adv0 + R);
         uint32_t nwalk = 0;
         {
-            uint32_t ai = adv0 + i0;
+            uint32_t ai = a_ip;
 #pragma unroll
             for (int o = 0; o < 4; o++) {
-                if (ai < alim) {  // uniform
+                if (ai < a_lim) {  // uniform
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         s->tagpos[o * 8 + k] = ai;
@@ -358,8 +374,7 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
         //      scan is a prefix operation and the group is cut at the first lane that is not `ok`.
         const uint32_t ak = s->tagpos[lane];
         const uint32_t a = sm_ld8(s, ak);
-        const uint32_t ik = ak - adv0;  // ring index (< R for every usable tag)
-        const uint32_t pk = ip + (ik - i0);
+        const uint32_t ik = ak - adv0;  // ring index (< R for every usable tag; the mirror covers ik + 1, ik + 2)
         const uint32_t c = s->ring[ik], b1 = s->ring[ik + 1], b2 = s->ring[ik + 2];
         const uint32_t n6 = c >> 2;
         const bool is_copy = (c & 3) != 0;
@@ -375,8 +390,8 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
         const uint32_t dst = op + (incl - len);
         // usable: landed + decodable; valid in stream order (SnappyDecompressor.cs:570-573,598-606 -- the one-tag path
         // names the error); the group stays below GMAX output bytes
-        const bool ok = lane < nwalk && a != 0 && pk + a <= landed_end && !(is_copy && off - 1u >= dst) &&
-                        len <= U - dst && dst <= U && incl <= GMAX;
+        const bool ok = lane < nwalk && a != 0 && ak + a <= a_land && !(is_copy && off - 1u >= dst) && dst + len <= U &&
+                        incl <= GMAX;
         const unsigned okm = __ballot_sync(SNP_FULL, ok);
         const uint32_t ng = okm == SNP_FULL ? 32u : (uint32_t)__ffs(~okm) - 1u;
         SNP7_STAT(ng);
@@ -387,67 +402,113 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
             break;
         }
         const uint32_t glen = __shfl_sync(SNP_FULL, incl, ng - 1);
-        const uint32_t ip_next = __shfl_sync(SNP_FULL, pk + a, ng - 1);
-        // descriptor of my tag for the rounds, in window coordinates wx = oskew + x:
-        //   bit 31 copy, bit 30 far (older than the window), bit 29 offset < 32 (may read bytes of its own round);
-        //   low 16 bits (mod 2^16): literal: ring index of byte 0 - wx(dst);  near copy: -offset;  far copy: offset.
-        const bool far = off > NEAR_MAX;
-        const uint32_t pack = !is_copy ? ((skew + pk + 1u - dst - oskew) & 0xffffu)
-                                       : (0x80000000u | (far ? 0x40000000u | off : (off < 32u ? 0x20000000u : 0u) | ((0u - off) & 0xffffu)));
-        const bool close = __any_sync(SNP_FULL, lane < ng && is_copy && off < 32u);
+        const uint32_t ip_next = ip + (__shfl_sync(SNP_FULL, ak + a, ng - 1) - a_ip);
+        const bool mine = lane < ng;
+        const uint32_t wxd = oskew + dst;  // window coordinate of my tag's first byte
+
+        // far back-references (older than the window) of <= 16 bytes: fetch the aligned words around the source from
+        // global memory now -- every lane's loads are in flight together, one memory latency per group -- and let the
+        // rounds read them from shared memory.  (Longer far copies are read byte-wise by the rounds.)
+        const bool far = mine && is_copy && off > NEAR_MAX;
+        const bool staged = far && len <= 16u;
+        const uint32_t gsrc = wxd - off;  // window coordinate of the source
+        if (__any_sync(SNP_FULL, staged)) {
+            const uint32_t *gp = reinterpret_cast<const uint32_t *>(out16 + (gsrc & ~3u));
+            const uint32_t nw = staged ? ((gsrc & 3u) + len + 3u) >> 2 : 0u;
+            uint32_t w[SNP7_STAGE_W];
+#pragma unroll
+            for (uint32_t j = 0; j < SNP7_STAGE_W; j++)
+                if (j < nw) w[j] = gp[j];
+#pragma unroll
+            for (uint32_t j = 0; j < SNP7_STAGE_W; j++)
+                if (j < nw) s->stage[lane * SNP7_STAGE_W + j] = w[j];
+        }
+        // descriptor of my tag for the rounds (t = wx + descriptor; only the low 16 bits of the sum are used):
+        //   literal / staged far copy: shared-memory byte (t & 0xffff), a linear address inside Warp7;
+        //   D_WIN: window byte t & (W-1) (low bits = -offset);  D_CLOSE: offset < 32, may read bytes of its own round;
+        //   D_GLOBAL: global byte out16[wx - (descriptor & 0xffff)] (low bits = offset).
+        const bool close = mine && is_copy && off < 32u;
+        uint32_t pack;
+        if (!is_copy) pack = (RING_OFF + ik + 1u - wxd) & 0xffffu;
+        else if (!far) pack = D_WIN | (close ? D_CLOSE : 0u) | ((0u - off) & 0xffffu);
+        else if (staged) pack = (STAGE_OFF + lane * (4u * SNP7_STAGE_W) + (gsrc & 3u) - wxd) & 0xffffu;
+        else pack = D_GLOBAL | off;
+        const bool any_global = __any_sync(SNP_FULL, far && !staged);
+        // rounds (of 32 output bytes) that hold a byte of a close copy resolve same-round sources by pointer doubling
+        uint32_t slow_rounds = 0;
+        if (__any_sync(SNP_FULL, close)) {
+            const uint32_t r0 = (dst - op) >> 5, r1 = (dst + len - 1u - op) >> 5;
+            slow_rounds = __reduce_or_sync(SNP_FULL, close ? (2u << r1) - (1u << r0) : 0u);
+        }
+        __syncwarp();  // the staged words are visible to every lane
 
         // ---- COPY: rounds of 32 output bytes, one byte per lane.  rel = start of my tag relative to the round.
-        uint32_t rel = lane < ng ? dst - op : 0xffffffffu;
+        uint32_t rel = mine ? dst - op : 0xffffffffu;
         uint32_t cm1 = 0xffffffffu;         // (tags that start in front of the round) - 1
         uint32_t wx = oskew + op + lane;    // my byte of the round, window coordinate
         const uint32_t wxe = oskew + op + glen;
-        if (!close) {
-            for (uint32_t n = (glen + 31u) >> 5; n; n--) {
-                const uint32_t M = __reduce_or_sync(SNP_FULL, shl_clamp(1u, rel));
-                rel -= 32u;
-                const uint32_t d = __shfl_sync(SNP_FULL, pack, cm1 + __popc(M & le));
-                cm1 += __popc(M);
-                const uint32_t t = wx + d;
-                const uint32_t si = (int32_t)d < 0 ? (t & (W - 1)) : (RING_OFF + (t & (R - 1)));
-                uint32_t v = sb[si];  // always inside the warp's shared memory
-                if ((d & 0x40000000u) && wx < wxe) v = out16[wx - (d & 0xffffu)];
-                if (wx < wxe) s->win[wx & (W - 1)] = (uint8_t)v;
-                wx += 32u;
-                __syncwarp();
+        auto fast_round = [&](const bool with_global) {
+            const uint32_t M = __reduce_or_sync(SNP_FULL, shl_clamp(1u, rel));
+            rel -= 32u;
+            const uint32_t d = __shfl_sync(SNP_FULL, pack, cm1 + __popc(M & le));
+            cm1 += __popc(M);
+            const uint32_t t = wx + d;
+            const uint32_t si = t & ((int32_t)d < 0 ? (W - 1) : 0xffffu);
+            const bool active = wx < wxe;
+            uint32_t v = 0;
+            if (with_global) {
+                if (active && !(d & D_GLOBAL)) v = sb[si];
+                if (active && (d & D_GLOBAL)) v = out16[wx - (d & 0xffffu)];
+            } else {
+                if (active) v = sb[si];
             }
+            if (active) s->win[wx & (W - 1)] = (uint8_t)v;
+            wx += 32u;
+            __syncwarp();
+        };
+        auto slow_round = [&]() {
+            const uint32_t M = __reduce_or_sync(SNP_FULL, shl_clamp(1u, rel));
+            rel -= 32u;
+            const uint32_t d = __shfl_sync(SNP_FULL, pack, cm1 + __popc(M & le));
+            cm1 += __popc(M);
+            const uint32_t t = wx + d;
+            const bool active = wx < wxe;
+            // source: sk 0 = shared-memory byte sa, 1 = global byte sa of out16, 2 = lane sa of this round
+            uint32_t sk = 0, sa = t & ((int32_t)d < 0 ? (W - 1) : 0xffffu);
+            if (d & D_GLOBAL) {
+                sk = 1;
+                sa = wx - (d & 0xffffu);
+            }
+            const uint32_t o5 = (0u - d) & 0xffffu;  // the offset of a close copy
+            if ((d & D_CLOSE) && o5 <= lane) {        // its source byte is produced in this round, by lane - offset
+                sk = 2;
+                sa = lane - o5;
+            }
+            if (!active) sk = 0, sa = 0;
+            while (__any_sync(SNP_FULL, sk == 2)) {  // pointer doubling, <= 5 trips (CopyHelpers.IncrementalCopy's
+                const uint32_t nk = __shfl_sync(SNP_FULL, sk, sa);  // pattern replication, any offset)
+                const uint32_t na = __shfl_sync(SNP_FULL, sa, sa);
+                if (sk == 2) {
+                    sk = nk;
+                    sa = na;
+                }
+            }
+            uint32_t v = sb[sk == 0 ? sa : 0u];
+            if (sk == 1 && active) v = out16[sa];
+            if (active) s->win[wx & (W - 1)] = (uint8_t)v;
+            wx += 32u;
+            __syncwarp();
+        };
+        const uint32_t nr = (glen + 31u) >> 5;
+        if (slow_rounds == 0) {
+            if (!any_global)
+                for (uint32_t n = nr; n; n--) fast_round(false);
+            else
+                for (uint32_t n = nr; n; n--) fast_round(true);
         } else {
-            for (uint32_t n = (glen + 31u) >> 5; n; n--) {
-                const uint32_t M = __reduce_or_sync(SNP_FULL, shl_clamp(1u, rel));
-                rel -= 32u;
-                const uint32_t d = __shfl_sync(SNP_FULL, pack, cm1 + __popc(M & le));
-                cm1 += __popc(M);
-                const uint32_t t = wx + d;
-                const bool active = wx < wxe;
-                // source: sk 0 = shared-memory byte sa (ring or window), 1 = global byte sa of out16, 2 = lane sa of this round
-                uint32_t sk = 0, sa = (int32_t)d < 0 ? (t & (W - 1)) : (RING_OFF + (t & (R - 1)));
-                if (d & 0x40000000u) {
-                    sk = 1;
-                    sa = wx - (d & 0xffffu);
-                }
-                const uint32_t o5 = (0u - d) & 0xffffu;  // the offset of a close copy
-                if ((d & 0x20000000u) && o5 <= lane) {    // its source byte is produced in this round, by lane - offset
-                    sk = 2;
-                    sa = lane - o5;
-                }
-                if (!active) sk = 0;
-                while (__any_sync(SNP_FULL, sk == 2)) {  // pointer doubling, <= 5 trips (CopyHelpers.IncrementalCopy's
-                    const uint32_t nk = __shfl_sync(SNP_FULL, sk, sa);  // pattern replication, any offset)
-                    const uint32_t na = __shfl_sync(SNP_FULL, sa, sa);
-                    if (sk == 2) {
-                        sk = nk;
-                        sa = na;
-                    }
-                }
-                uint32_t v = sb[sk == 0 ? sa : 0u];
-                if (sk == 1 && active) v = out16[sa];
-                if (active) s->win[wx & (W - 1)] = (uint8_t)v;
-                wx += 32u;
-                __syncwarp();
+            for (uint32_t n = nr; n; n--, slow_rounds >>= 1) {
+                if (slow_rounds & 1u) slow_round();
+                else fast_round(true);
             }
         }
         op += glen;
@@ -464,8 +525,8 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
 
 #ifndef SNP_EMU
 // Persistent launch: every warp pulls the next block index from a global counter (cheap and expensive blocks balance).
-template <uint32_t W, int CTAS>
-__global__ void __launch_bounds__(256, CTAS)
+template <uint32_t W, int NW, int CTAS>  // window bytes per warp, warps per CTA, CTAs per SM
+__global__ void __launch_bounds__(NW * 32, CTAS)
 k_decompress_v7(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
                 const uint32_t *__restrict__ in_len, uint8_t *out_base, const uint64_t *__restrict__ out_off,
                 const uint32_t *__restrict__ out_cap, uint32_t *__restrict__ out_len, int32_t *__restrict__ status,

@@ -101,7 +101,9 @@ struct snp_ctx {
     int decomp_kernel = 7;  // SNP_DECOMP_KERNEL: 7 = tag-group engine (TMA-staged input ring, advance-table walk, output
                             // window; the default), 5 = the round-1 default (sparse-tag prefix engine + speculative
                             // dense engine; kept as the A/B challenger), 1 = warp-uniform baseline
-    int v7_window = 2048;   // SNP_V7_WINDOW: output window bytes per warp of k_decompress_v7 (2048: 48 warps per SM, 4096: 32)
+    int v7_window = 4096;   // SNP_V7_WINDOW: output window bytes per warp of k_decompress_v7: 4096 (32 warps per SM, the
+                            // default), 2048 (40 warps; 48 with SNP_V7_CTAS=6), 8192 (20 warps)
+    int v7_ctas = 0;        // SNP_V7_CTAS
     int comp_kernel = 3;    // SNP_COMP_KERNEL (1 = baseline, 2 = smem tables, 3 = L2 tables, 4 = 3 + register window,
                             // 5 = two blocks per warp (half-warps): measured 10-15 % slower than 3, DESIGN.md 4.6;
                             // 4 measured equal to 3: the kernel is bound by random table sectors)
@@ -151,10 +153,14 @@ int ctx_set_attrs(snp_ctx *c) {
                             (int)kComp2Smem));
     CU(cudaFuncSetAttribute(snp::k_compress_v2<SNP_HASH_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kComp2Smem));
-    CU(cudaFuncSetAttribute(snp::k_decompress_v7<2048, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(8 * sizeof(snp::Warp7<2048>))));
-    CU(cudaFuncSetAttribute(snp::k_decompress_v7<4096, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(8 * sizeof(snp::Warp7<4096>))));
+#define SNP7_ATTR(W, NW, CTAS)                                                                              \
+    CU(cudaFuncSetAttribute(snp::k_decompress_v7<W, NW, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                            (int)(NW * sizeof(snp::Warp7<W>))))
+    SNP7_ATTR(2048, 8, 5);
+    SNP7_ATTR(2048, 8, 6);
+    SNP7_ATTR(4096, 8, 4);
+    SNP7_ATTR(8192, 4, 5);
+#undef SNP7_ATTR
 
     c->attrs_set = true;
     return SNP_OK;
@@ -193,15 +199,17 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
         if (rc) return rc;
         unsigned long long *ctr;
         if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
-        if (c->v7_window == 4096) {
-            const unsigned pgrid = std::min(grid, (unsigned)(c->sm_count * 4));
-            snp::k_decompress_v7<4096, 4><<<pgrid, warps * SNP_WARP, 8 * sizeof(snp::Warp7<4096>), s>>>(
-                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, ctr);
-        } else {
-            const unsigned pgrid = std::min(grid, (unsigned)(c->sm_count * 6));
-            snp::k_decompress_v7<2048, 6><<<pgrid, warps * SNP_WARP, 8 * sizeof(snp::Warp7<2048>), s>>>(
-                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, ctr);
-        }
+#define SNP7_LAUNCH(W, NW, CTAS)                                                                                  \
+    do {                                                                                                          \
+        const unsigned g7 = std::min((unsigned)((n + NW - 1) / NW), (unsigned)(c->sm_count * CTAS));              \
+        snp::k_decompress_v7<W, NW, CTAS><<<g7, NW * SNP_WARP, NW * sizeof(snp::Warp7<W>), s>>>(                  \
+            in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, ctr);                       \
+    } while (0)
+        if (c->v7_window == 8192) SNP7_LAUNCH(8192, 4, 5);        // 20 warps per SM, 8 KiB windows
+        else if (c->v7_window == 2048 && c->v7_ctas == 6) SNP7_LAUNCH(2048, 8, 6);  // 48 warps per SM (40 registers)
+        else if (c->v7_window == 2048) SNP7_LAUNCH(2048, 8, 5);   // 40 warps per SM
+        else SNP7_LAUNCH(4096, 8, 4);                             // 32 warps per SM, 4 KiB windows (default)
+#undef SNP7_LAUNCH
     } else if (kernel == 1)
         snp::k_decompress_v1<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
                                                                out_cap, out_len, status, n);
@@ -759,7 +767,8 @@ int snp_create(int device, snp_ctx **out) {
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 7);
-    c->v7_window = env_int("SNP_V7_WINDOW", 2048);
+    c->v7_window = env_int("SNP_V7_WINDOW", 4096);
+    c->v7_ctas = env_int("SNP_V7_CTAS", 0);
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));

@@ -7,6 +7,11 @@ static unsigned long g_groups, g_group_tags, g_slow;  // fast-path coverage, pri
 #define SNP7_STAT(ng) do { if (simt::lane() == 0) { if (ng) { g_groups++; g_group_tags += (ng); } else g_slow++; } } while (0)
 #include "../../snappier_b200/csrc/snp_decompress_v7.cuh"
 
+#include <execinfo.h>
+#include <signal.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include <vector>
 
 static std::vector<uint8_t> slurp(const char *p) {
@@ -22,6 +27,16 @@ static std::vector<uint8_t> slurp(const char *p) {
     if (n && fread(v.data(), 1, n, f) != (size_t)n) exit(2);
     fclose(f);
     return v;
+}
+
+static uint8_t *g_smem;
+static size_t g_ssz;
+static void on_segv(int, siginfo_t *si, void *) {  // says where a lane left the warp's shared memory
+    fprintf(stderr, "emu_v7: fault at shared-memory offset %ld (struct size %zu), lane %d\n",
+            (long)((uint8_t *)si->si_addr - g_smem), g_ssz, simt::lane());
+    void *bt[32];
+    backtrace_symbols_fd(bt, backtrace(bt, 32), 2);
+    _exit(139);
 }
 
 template <uint32_t W>
@@ -48,8 +63,25 @@ int main(int argc, char **argv) {
     uint32_t n;
     memcpy(&n, p, 4);
     p += 4;
-    void *smem = aligned_alloc(16, sizeof(snp::Warp7<4096>));
-    memset(smem, 0x5a, sizeof(snp::Warp7<4096>));  // stale garbage, like shared memory
+    // the warp's shared memory ends at a PROT_NONE page, so an access behind its struct faults here as it would on the
+    // GPU for the last warp of a CTA; the content starts as garbage, like shared memory
+    const size_t ssz = window == 1024 ? sizeof(snp::Warp7<1024>) : window == 2048 ? sizeof(snp::Warp7<2048>) : sizeof(snp::Warp7<4096>);
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE), span = (ssz + page - 1) / page * page;
+    uint8_t *region = (uint8_t *)mmap(nullptr, span + 2 * page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (region == MAP_FAILED) return 2;
+    mprotect(region, page, PROT_NONE);
+    mprotect(region + page + span, page, PROT_NONE);
+    void *smem = region + page + span - ssz;  // 16-byte aligned: sizeof is a multiple of 16
+    memset(smem, 0xff, ssz);
+    g_smem = (uint8_t *)smem;
+    g_ssz = ssz;
+    struct sigaction sa = {};
+    sa.sa_sigaction = on_segv;
+    sa.sa_flags = SA_SIGINFO | SA_ONSTACK;
+    static uint8_t altstack[1 << 16];
+    stack_t ss = {altstack, 0, sizeof(altstack)};
+    sigaltstack(&ss, nullptr);
+    sigaction(SIGSEGV, &sa, nullptr);
     auto init = [&](auto *s) {  // what the kernel prologue does
         simt::run_warp([&] { snp::warp7_init(s, (unsigned)simt::lane()); });
     };
@@ -85,6 +117,5 @@ int main(int argc, char **argv) {
     if (getenv("SNP7_EMU_STATS"))
         fprintf(stderr, "emu_v7: %lu groups, %.1f tags per group, %lu one-tag steps\n", g_groups,
                 g_groups ? (double)g_group_tags / g_groups : 0.0, g_slow);
-    free(smem);
     return 0;
 }

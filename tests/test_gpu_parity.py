@@ -337,8 +337,8 @@ def test_device_mode_large_batch_properties(engine, oracle):
     ch = comp.view(n, pitch)
     for i in (0, 1, 63, 64, 2047, 4095):
         assert ch[i, : cl[i]].cpu().numpy().tobytes() == oracle.compress(blocks[i % len(blocks)])[1]
-    # the 4 KiB-window instantiation of the default kernel and the round-1 kernel on the same device-resident batch
-    for env in ({"SNP_V7_WINDOW": "4096"}, {"SNP_DECOMP_KERNEL": "5"}):
+    # the 2 KiB-window instantiation of the default kernel and the round-1 kernel on the same device-resident batch
+    for env in ({"SNP_V7_WINDOW": "2048"}, {"SNP_DECOMP_KERNEL": "5"}):
         ex = _engine_with(env)
         out.zero_()
         o_len.zero_()
@@ -371,8 +371,8 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     and statuses on corpus blocks, synthetic blocks and corrupted blocks."""
     from snappier_b200.batch import compress_many, decompress_many
     e1 = _engine_with({"SNP_DECOMP_KERNEL": "1", "SNP_COMP_KERNEL": "1"})
-    e2 = _engine_with({})                            # default: tag-group engine, 2 KiB output window
-    e4 = _engine_with({"SNP_V7_WINDOW": "4096"})     # the same engine with a 4 KiB window (32 warps per SM)
+    e2 = _engine_with({})                            # default: tag-group engine, 4 KiB output window
+    e4 = _engine_with({"SNP_V7_WINDOW": "2048"})     # the same engine with a 2 KiB window (40 warps per SM)
     e5 = _engine_with({"SNP_DECOMP_KERNEL": "5"})    # round-1 default: sparse-tag prefix engine + speculative dense engine
     _, blocks = _corpus_blocks(fixtures)
     blocks = blocks + H.synthetic_blocks(5150, 48)
@@ -421,7 +421,7 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
         ex.close()
 
 
-@pytest.mark.parametrize("env", [{}, {"SNP_V7_WINDOW": "4096"}])
+@pytest.mark.parametrize("env", [{}, {"SNP_V7_WINDOW": "2048"}])
 def test_ragged_blocks_work_stealing_and_dense_tags(oracle, fixtures, env):
     """The default kernel on thousands of ragged blocks that share 16-byte output vectors with their neighbours (the
     window flush must not touch a neighbour's bytes) and on a block of > 24 576 tiny tags."""
@@ -451,7 +451,7 @@ def test_ragged_blocks_work_stealing_and_dense_tags(oracle, fixtures, env):
     e6.close()
 
 
-@pytest.mark.parametrize("env", [{}, {"SNP_V7_WINDOW": "4096"}])
+@pytest.mark.parametrize("env", [{}, {"SNP_V7_WINDOW": "2048"}])
 def test_handmade_tag_forms_and_fuzz(oracle, env):
     """The default kernel on the hand-assembled tag forms the emulator tests use (COPY4, literal-length forms, literals
     > 64 bytes at every position of a tag group, every offset 1..40 x lengths around 16 / 32 / 64) and on mutated

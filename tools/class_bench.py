@@ -73,7 +73,7 @@ def time_decompress(torch, engine, comp, c_off, c_len, sums, weights, n, dev, re
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blocks", type=int, default=1 << 15)
-    ap.add_argument("--variants", default="7,7w4096,5")
+    ap.add_argument("--variants", default="7,7w2048,5")
     ap.add_argument("--small", default="64,256,1024,4096")
     ap.add_argument("--classes", default="", help="comma-separated subset of class names (default: all)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "class_bench.json"))
@@ -84,7 +84,8 @@ def main():
     variants = args.variants.split(",")
     def env_of(v):  # "7" = default kernel, "7w4096" = its 4 KiB-window instantiation, "5" = the round-1 kernel
         k, _, w = v.partition("w")
-        return {"SNP_DECOMP_KERNEL": k, "SNP_V7_WINDOW": w or "2048"}
+        w, _, c = w.partition("c")
+        return {"SNP_DECOMP_KERNEL": k, "SNP_V7_WINDOW": w or "4096", "SNP_V7_CTAS": c or "0"}
     engines = {v: engine_with(env_of(v)) for v in variants}
     prep_engine = engines[variants[0]]
     res = {"blocks": args.blocks, "classes": {}, "small_mix": {}}
