@@ -24,6 +24,7 @@
 #include "snp_decompress_v3.cuh"
 #include "snp_decompress_v5.cuh"
 #include "snp_decompress_v7.cuh"
+#include "snp_decompress_v8.cuh"
 #include "snp_frame.cuh"
 
 namespace {
@@ -104,6 +105,7 @@ struct snp_ctx {
     int v7_window = 4096;   // SNP_V7_WINDOW: output window bytes per warp of k_decompress_v7: 4096 (32 warps per SM, the
                             // default), 2048 (40 warps; 48 with SNP_V7_CTAS=6), 8192 (20 warps)
     int v7_ctas = 0;        // SNP_V7_CTAS
+    int v8_cfg = 0;         // SNP_V8_CFG: lane-per-block engine instantiation (see launch_decompress)
     int comp_kernel = 3;    // SNP_COMP_KERNEL (1 = baseline, 2 = smem tables, 3 = L2 tables, 4 = 3 + register window,
                             // 5 = two blocks per warp (half-warps): measured 10-15 % slower than 3, DESIGN.md 4.6;
                             // 4 measured equal to 3: the kernel is bound by random table sectors)
@@ -161,6 +163,18 @@ int ctx_set_attrs(snp_ctx *c) {
     SNP7_ATTR(4096, 8, 4);
     SNP7_ATTR(8192, 4, 5);
 #undef SNP7_ATTR
+#define SNP8_ATTR(IR, ORB, D, NT, CTAS, ...)                                                                              \
+    CU(cudaFuncSetAttribute(snp::k_decompress_v8<IR, ORB, D, NT, CTAS, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                            (int)(NT * sizeof(snp::Lane8<IR, ORB, D>))))
+    SNP8_ATTR(128, 128, 3, 96, 6);
+    SNP8_ATTR(128, 128, 3, 128, 4);
+    SNP8_ATTR(128, 128, 4, 128, 4);
+    SNP8_ATTR(128, 128, 2, 96, 6);
+    SNP8_ATTR(256, 256, 3, 64, 5);
+    SNP8_ATTR(128, 128, 3, 96, 6, 1);
+    SNP8_ATTR(128, 128, 4, 64, 4, 1);
+    SNP8_ATTR(128, 128, 4, 64, 2, 1);
+#undef SNP8_ATTR
 
     c->attrs_set = true;
     return SNP_OK;
@@ -210,6 +224,26 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
         else if (c->v7_window == 2048) SNP7_LAUNCH(2048, 8, 5);   // 40 warps per SM
         else SNP7_LAUNCH(4096, 8, 4);                             // 32 warps per SM, 4 KiB windows (default)
 #undef SNP7_LAUNCH
+    } else if (kernel == 8) {
+        int rc = ctx_set_attrs(c);
+        if (rc) return rc;
+        unsigned long long *ctr;
+        if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
+#define SNP8_LAUNCH(IR, ORB, D, NT, CTAS, ...)                                                                    \
+    do {                                                                                                          \
+        const unsigned g8 = std::min((unsigned)((n + NT - 1) / NT), (unsigned)(c->sm_count * CTAS));              \
+        snp::k_decompress_v8<IR, ORB, D, NT, CTAS, ##__VA_ARGS__><<<g8, NT, NT * sizeof(snp::Lane8<IR, ORB, D>), s>>>( \
+            in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, ctr);                       \
+    } while (0)
+        if (c->v8_cfg == 1) SNP8_LAUNCH(128, 128, 3, 128, 4);       // 512 lanes per SM
+        else if (c->v8_cfg == 2) SNP8_LAUNCH(128, 128, 4, 128, 4);  // deeper pipeline
+        else if (c->v8_cfg == 3) SNP8_LAUNCH(128, 128, 2, 96, 6);   // shallower pipeline
+        else if (c->v8_cfg == 4) SNP8_LAUNCH(256, 256, 3, 64, 5);   // 320 lanes per SM, 256-byte rings
+        else if (c->v8_cfg == 5) SNP8_LAUNCH(128, 128, 3, 96, 6, 1);  // 576 lanes, read-once lines evict first
+        else if (c->v8_cfg == 6) SNP8_LAUNCH(128, 128, 4, 64, 4, 1);  // 256 lanes per SM, depth 4, evict first
+        else if (c->v8_cfg == 7) SNP8_LAUNCH(128, 128, 4, 64, 2, 1);  // 128 lanes per SM, depth 4, evict first
+        else SNP8_LAUNCH(128, 128, 3, 96, 6);                       // 576 lanes per SM, 128-byte rings, depth 3
+#undef SNP8_LAUNCH
     } else if (kernel == 1)
         snp::k_decompress_v1<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
                                                                out_cap, out_len, status, n);
@@ -769,6 +803,13 @@ int snp_create(int device, snp_ctx **out) {
     c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 7);
     c->v7_window = env_int("SNP_V7_WINDOW", 4096);
     c->v7_ctas = env_int("SNP_V7_CTAS", 0);
+    c->v8_cfg = env_int("SNP_V8_CFG", 0);
+    if (const int l2g = env_int("SNP_L2_FETCH", 0)) {  // experiment: DRAM -> L2 fetch granularity (32 / 64 / 128 bytes)
+        CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2g));
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        if (env_int("SNP_HOST_TRACE", 0)) fprintf(stderr, "snappier_b200: L2 fetch granularity %zu\n", got);
+    }
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));

@@ -85,6 +85,8 @@ def main():
     def env_of(v):  # "7" = default kernel, "7w4096" = its 4 KiB-window instantiation, "5" = the round-1 kernel
         k, _, w = v.partition("w")
         w, _, c = w.partition("c")
+        if k.startswith("8"):  # "8" = lane-per-block engine, "8c1" / "8c2" = its other instantiations (SNP_V8_CFG)
+            return {"SNP_DECOMP_KERNEL": "8", "SNP_V8_CFG": c or "0"}
         return {"SNP_DECOMP_KERNEL": k, "SNP_V7_WINDOW": w or "4096", "SNP_V7_CTAS": c or "0"}
     engines = {v: engine_with(env_of(v)) for v in variants}
     prep_engine = engines[variants[0]]
