@@ -31,6 +31,8 @@ sys.path.insert(0, ROOT)
 BLOCK = 65536
 PITCH = 76496  # Snappy.GetMaxCompressedLength(65536)
 METRIC = "uncompressed GB/s (batched decompress, 64 KiB blocks)"
+DECOMPRESS_KERNEL = "snp::k_decompress_v7<4096, 8, 4>"   # the launches behind `value` (profiles/r02_launches.md)
+COMPRESS_KERNEL = "snp::k_compress_v3<SNP_HASH_CRC32C, 3>"
 WORKLOAD = "batched decompress: 2^20 x 64 KiB precompressed blocks per GPU (Silesia-mix synthetic), device-resident"
 
 
@@ -266,11 +268,15 @@ def dotnet_probe():
 
 
 def host_sample_blocks(n_blocks: int, first_block: int = 0):
-    """CPU-only construction of a bounded sample of the workload for --impl reference (no GPU)."""
+    """CPU-only construction of a bounded sample of the workload for --impl reference (no GPU): raw blocks of the
+    config-2 mixture, compressed with the oracle.  Returns (slots, offs, lens)."""
     import torch
     from oracle import pyoracle as O
     corpus = {k: torch.from_numpy(v) for k, v in load_corpus().items()}
-    raw = make_blocks(torch, corpus, first_block, n_blocks, torch.device("cpu")).numpy()
+    raw = np.empty((n_blocks, BLOCK), np.uint8)
+    for b0 in range(0, n_blocks, 8192):
+        m = min(8192, n_blocks - b0)
+        raw[b0:b0 + m] = make_blocks(torch, corpus, first_block + b0, m, torch.device("cpu")).numpy()
     caps = np.full(n_blocks, PITCH, np.uint32)
     offs = np.arange(n_blocks, dtype=np.uint64) * PITCH
     slots = np.empty(n_blocks * PITCH, np.uint8)
@@ -281,9 +287,13 @@ def host_sample_blocks(n_blocks: int, first_block: int = 0):
 
 
 def run_reference(args):
+    """The reference arm: the reference's CPU implementation of the path (the oracle C port of Snappier's algorithm --
+    no .NET in this image) on all host cores, on a bounded sample of the same workloads: decompress (config 2, the
+    line's value) and compress (config 3, the `compress` object)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
     from oracle import pyoracle as O
     O.build()
     threads = os.cpu_count() or 1
@@ -300,7 +310,29 @@ def run_reference(args):
         assert bad == 0
     dt = time.perf_counter() - t0
     val = args.steps * n * BLOCK / dt / 1e9
-    sample = f"{n} blocks of the same synthetic mix per step, {threads} pthreads, oracle C port of the reference (no .NET in this image)"
+    del slots, out
+    # compress arm: config-3 blocks
+    nc = min(n, args.ref_compress_blocks)
+    raw = np.empty((nc, BLOCK), np.uint8)
+    for b0 in range(0, nc, 8192):
+        m = min(8192, nc - b0)
+        raw[b0:b0 + m] = make_blocks_config3(torch, b0, m, torch.device("cpu")).numpy()
+    raw = raw.reshape(-1)
+    cslots = np.empty(nc * PITCH, np.uint8)
+    r_off = np.arange(nc, dtype=np.uint64) * BLOCK
+    r_len = np.full(nc, BLOCK, np.uint32)
+    s_off = np.arange(nc, dtype=np.uint64) * PITCH
+    s_cap = np.full(nc, PITCH, np.uint32)
+    for _ in range(args.warmup):
+        O.compress_batch(raw, r_off, r_len, cslots, s_off, s_cap, 0, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bad, clens, _ = O.compress_batch(raw, r_off, r_len, cslots, s_off, s_cap, 0, threads)
+        assert bad == 0
+    cdt = time.perf_counter() - t0
+    cval = args.steps * nc * BLOCK / cdt / 1e9
+    how = f"{threads} pthreads, oracle C port of the reference (no .NET in this image)"
+    sample = f"{n} blocks of the same synthetic mix per step, {how}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
@@ -308,67 +340,193 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "sample_blocks": n},
         "cpu_baseline": {"value": round(val, 3), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "compress": {"metric": "uncompressed GB/s (batched compress, 64 KiB blocks)", "value": round(cval, 3), "unit": "GB/s",
+                     "ms_per_step": round(cdt / args.steps * 1e3, 3),
+                     "config": {"workload": "batched compress: 64 KiB raw blocks (50 % compressible synthetic)", "sample_blocks": nc,
+                                "ratio": round(float(clens.astype(np.int64).sum()) / (nc * BLOCK), 4), "hash_mode": "crc32c"},
+                     "cpu_baseline": {"value": round(cval, 3), "unit": "GB/s", "cores": threads, "kind": "port",
+                                      "sample": f"{nc} config-3 blocks per step, {how}"},
+                     "e2e": {"value": round(cval, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
         "gpu_launches": 0,
     }))
 
 
-def run_compress(args, torch, dist, engine, world, rank, local, dev):
-    """BASELINE config 3: batched compress of raw 64 KiB blocks (extra line; not the driver's headline)."""
-    n = min(args.blocks, 1 << 19)  # raw + worst-case slots must fit: 2^19 x (64 KiB + 76496 B) = 74 GB
+def hbm_peak():
+    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pp):
+        return float(json.load(open(pp))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_per_block(key):
+    """DRAM bytes per block of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json)."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tp):
+        return None, None
+    j = json.load(open(tp))
+    return j.get(key), j.get("source")
+
+
+def cpu_compress_run(raw_host: np.ndarray, n: int, threads: int, min_seconds: float):
+    """Times the oracle's multi-threaded batched compress (CRC32C hash mode) on n raw blocks held on the host."""
+    from oracle import pyoracle as O
+    slots = np.empty(n * PITCH, np.uint8)
+    r_off = np.arange(n, dtype=np.uint64) * BLOCK
+    r_len = np.full(n, BLOCK, np.uint32)
+    s_off = np.arange(n, dtype=np.uint64) * PITCH
+    s_cap = np.full(n, PITCH, np.uint32)
+    O.compress_batch(raw_host, r_off, r_len, slots, s_off, s_cap, 0, threads)  # warm
+    t0 = time.perf_counter()
+    passes = 0
+    while True:
+        bad, lens, _ = O.compress_batch(raw_host, r_off, r_len, slots, s_off, s_cap, 0, threads)
+        assert bad == 0
+        passes += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return passes * n * BLOCK / dt / 1e9, passes, dt
+
+
+def compress_section(args, torch, dist, engine, world, rank, local, dev):
+    """BASELINE config 3: batched compress of 2^20 raw 64 KiB blocks per GPU ('50 % compressible synthetic').  The raw
+    blocks are resident in HBM; the worst-case output slots (76 496 B each) of 2^20 blocks would need another 80 GB, so
+    the step STREAMS them: the batch goes through the C ABI in launches of 2^19 blocks that reuse one slot buffer (the
+    consumer of a real pipeline would drain it in between).  Returns rank 0's dict (None elsewhere)."""
+    n = args.blocks
+    chunk = min(n, 1 << 19)
+    nch = (n + chunk - 1) // chunk
     raw = torch.empty((n, BLOCK), dtype=torch.uint8, device=dev)
     for b0 in range(0, n, 8192):
         m = min(8192, n - b0)
         raw[b0:b0 + m] = make_blocks_config3(torch, rank * n + b0, m, dev)
-    slots = torch.empty(n * PITCH, dtype=torch.uint8, device=dev)
-    idx = torch.arange(n, device=dev, dtype=torch.int64)
+    slots = torch.empty(chunk * PITCH, dtype=torch.uint8, device=dev)
+    idx = torch.arange(chunk, device=dev, dtype=torch.int64)
     r_off, s_off = idx * BLOCK, idx * PITCH
-    r_len = torch.full((n,), BLOCK, dtype=torch.int32, device=dev)
-    s_cap = torch.full((n,), PITCH, dtype=torch.int32, device=dev)
-    s_len = torch.zeros(n, dtype=torch.int32, device=dev)
-    st = torch.zeros(n, dtype=torch.int32, device=dev)
+    r_len = torch.full((chunk,), BLOCK, dtype=torch.int32, device=dev)
+    s_cap = torch.full((chunk,), PITCH, dtype=torch.int32, device=dev)
+    s_len = torch.zeros((nch, chunk), dtype=torch.int32, device=dev)
+    st = torch.zeros((nch, chunk), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    flat = raw.view(-1)
 
     def step():
-        engine.compress_batch_device(raw.view(-1), r_off, r_len, slots, s_off, s_cap, s_len, st, 0, stream)
+        for c in range(nch):
+            m = min(chunk, n - c * chunk)
+            engine.compress_batch_device(flat[c * chunk * BLOCK:], r_off[:m], r_len[:m], slots, s_off[:m], s_cap[:m],
+                                         s_len[c, :m], st[c, :m], 0, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = engine.launch_count
     with ClockSampler(local) as clk:
+        barrier()
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
-        torch.cuda.synchronize()
+        barrier()
     ms = e0.elapsed_time(e1) / args.steps
-    assert int(st.abs().sum()) == 0
+    launches = engine.launch_count - launches0
+    assert int(st.abs().sum()) == 0, "compress reported errors"
     cbytes = int(s_len.to(torch.int64).sum())
-    # parity on a sample against the oracle (outside the timed region)
+    # the slots hold the LAST launch's blocks: decompress them and compare with the raw blocks (bit-exact round trip),
+    # and compare a sample with the oracle's compressed bytes (outside the timed region)
+    c0 = (nch - 1) * chunk
+    m = n - c0
+    back = torch.empty(m * BLOCK, dtype=torch.uint8, device=dev)
+    o_len = torch.zeros(m, dtype=torch.int32, device=dev)
+    st2 = torch.zeros(m, dtype=torch.int32, device=dev)
+    engine.decompress_batch_device(slots, s_off[:m], s_len[nch - 1, :m], back, r_off[:m], r_len[:m], o_len, st2, stream)
+    torch.cuda.synchronize()
+    assert int(st2.abs().sum()) == 0 and torch.equal(back, flat[c0 * BLOCK:]), "compressed blocks do not round-trip"
+    del back
     from oracle import pyoracle as O
-    sl = s_len.cpu().numpy()
-    for i in list(range(0, n, max(1, n // 64)))[:64]:
-        assert slots[i * PITCH: i * PITCH + int(sl[i])].cpu().numpy().tobytes() == O.compress(raw[i].cpu().numpy().tobytes())[1]
-    peak = 6550.4
-    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pp):
-        peak = float(json.load(open(pp))["hbm_gbs"])
-    ctraffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        pb = json.load(open(tp)).get("compress_dram_bytes_per_block")
-        ctraffic = int(pb * n) if pb else None
-    if rank == 0:
-        print(json.dumps({
-            "metric": "uncompressed GB/s (batched compress, 64 KiB blocks)", "value": round(n * BLOCK / ms / 1e6, 2),
-            "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"batched compress: {n} x 64 KiB raw blocks per GPU (50 % compressible synthetic), device-resident",
-                       "ratio": round(cbytes / (n * BLOCK), 4), "hash_mode": "crc32c"},
-            "roofline": {"bound": "hbm", "achieved": round((n * BLOCK + cbytes) / ms / 1e6, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round((n * BLOCK + cbytes) / ms / 1e6 / peak, 4), "traffic": ctraffic, "kernel": "snp::k_compress_v3"},
-            "gpu_launches": args.steps, "clocks": clk.summary()}))
+    sl = s_len[nch - 1].cpu().numpy()
+    for i in list(range(0, m, max(1, m // 64)))[:64]:
+        assert slots[i * PITCH: i * PITCH + int(sl[i])].cpu().numpy().tobytes() == O.compress(raw[c0 + i].cpu().numpy().tobytes())[1], \
+            "compressed bytes differ from the oracle"
 
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    b = torch.tensor([float(n) * BLOCK, float(cbytes)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+
+    # ---- e2e through the C ABI with pinned HOST buffers (H2D + kernel + D2H timed) ----
+    ne = min(args.e2e_blocks, n)
+    h_raw = torch.empty(ne * BLOCK, dtype=torch.uint8).pin_memory()
+    h_raw.copy_(flat[:ne * BLOCK])
+    h_slots = torch.empty(ne * PITCH, dtype=torch.uint8).pin_memory()
+    hr_off = np.arange(ne, dtype=np.uint64) * BLOCK
+    hr_len = np.full(ne, BLOCK, np.uint32)
+    hs_off = np.arange(ne, dtype=np.uint64) * PITCH
+    hs_cap = np.full(ne, PITCH, np.uint32)
+    np_raw, np_slots = h_raw.numpy(), h_slots.numpy()
+    for _ in range(2):
+        engine.compress_batch_host(np_raw, hr_off, hr_len, np_slots, hs_off, hs_cap, 0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        ol, est = engine.compress_batch_host(np_raw, hr_off, hr_len, np_slots, hs_off, hs_cap, 0)
+    torch.cuda.synchronize()
+    e_dt = (time.perf_counter() - t0) / e2e_steps
+    assert not est.any() and np.array_equal(ol, s_len[0, :ne].cpu().numpy().astype(ol.dtype))
+    te = torch.tensor([e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * ne * BLOCK / float(te[0]) / 1e9
+    e_cbytes = int(ol.astype(np.int64).sum())
+    if rank != 0:
+        return None
+    ms = float(t[0])
+    u, cb = float(b[0]), float(b[1])
+    peak, peak_src = hbm_peak()
+    alg = float(n) * BLOCK + float(cbytes)  # rank 0's step: U read + C written
+    per_block, tsrc = traffic_per_block("compress_dram_bytes_per_block")
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        nc = min(args.cpu_blocks, n)
+        threads = os.cpu_count() or 1
+        v, passes, dt = cpu_compress_run(flat[:nc * BLOCK].cpu().numpy(), nc, threads, args.cpu_seconds)
+        cpu = {"value": round(v, 3), "unit": "GB/s", "cores": threads, "kind": "port",
+               "sample": f"first {nc} blocks of rank 0's batch, {passes} passes in {dt:.1f} s, oracle C port of the reference "
+                         "compressor (CRC32C hash mode; Snappier's C# cannot run here)"}
+    return {
+        "metric": "uncompressed GB/s (batched compress, 64 KiB blocks)", "value": round(u / ms / 1e6, 2), "unit": "GB/s",
+        "ms_per_step": round(ms, 4),
+        "config": {"workload": f"batched compress: {n} x 64 KiB raw blocks per GPU (50 % compressible synthetic), device-resident, "
+                               f"streamed as {nch} launches of {chunk} blocks through one slot buffer",
+                   "ratio": round(cb / u, 4), "hash_mode": "crc32c"},
+        "roofline": {"bound": "hbm", "achieved": round(alg / ms / 1e6, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(alg / ms / 1e6 / peak, 4), "traffic": int(per_block * n) if per_block else None,
+                     "traffic_source": tsrc, "peak_source": peak_src, "kernel": COMPRESS_KERNEL,
+                     "algorithmic_bytes_per_step": int(alg)},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(e2e_val, 3), "unit": "GB/s", "h2d_bytes_per_step": int(ne * BLOCK + ne * 24),
+                "d2h_bytes_per_step": int(e_cbytes + ne * 8), "blocks_per_step": ne,
+                "path": "snp_compress_batch(SNP_MEM_HOST) on pinned host buffers"},
+        "gpu_launches": int(launches), "clocks": clk.summary()}
+
+
+def run_compress(args, torch, dist, engine, world, rank, local, dev):
+    """--workload compress: config 3 as a line of its own."""
+    sec = compress_section(args, torch, dist, engine, world, rank, local, dev)
+    if rank == 0:
+        line = {"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic"}
+        line.update(sec)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_frame(args, torch, engine, rank, local, dev):
@@ -435,21 +593,30 @@ def run_frame(args, torch, engine, rank, local, dev):
         "clocks": clk.summary()}))
 
 
-def run_roundtrip(args, torch, dist, engine, world, rank, local, dev):
-    """BASELINE config 5: mixed-block corpus (config-2 mixture and config-3 blocks 1:1) sharded by contiguous block
-    range across the GPUs, compress then decompress, verified by per-block checksums.  `value` is the born-sharded
-    round trip (no data-path collective); with N > 1 a root-sourced scatter of the raw blocks and a gather(v) of the
-    compressed blocks over NCCL are timed on a sample beside it (link-bound).  Extra line."""
-    n = min(args.blocks, 1 << 17)  # 8 GiB raw per GPU (64 GiB at 8 GPUs)
+def roundtrip_section(args, torch, dist, engine, world, rank, local, dev):
+    """BASELINE config 5: mixed-block corpus (config-2 mixture and config-3 blocks 1:1), 2^17 blocks = 8 GiB per GPU
+    (64 GiB at 8 GPUs), sharded by contiguous block range, compress then decompress, verified by per-block checksums.
+    Two measurements:
+      * born sharded: every rank holds its shard already; no data-path collective (`value`);
+      * root-sourced (N > 1): rank 0 holds the whole corpus; ONE scatter of the raw block ranges over NCCL, compress,
+        decompress, ONE gather(v) of the packed compressed blocks back to rank 0 -- bound by rank 0's NVLink egress /
+        ingress, reported per phase (`nccl_scatter_gather`).
+    Returns rank 0's dict (None elsewhere)."""
+    n = min(args.blocks, 1 << 17)
     corpus_dev = {k: torch.from_numpy(v).to(dev) for k, v in load_corpus().items()}
-    raw = torch.empty((n, BLOCK), dtype=torch.uint8, device=dev)
-    for b0 in range(0, n, 8192):
-        m = min(8192, n - b0)
-        a = make_blocks(torch, corpus_dev, rank * n + b0, m, dev)
-        c3 = make_blocks_config3(torch, rank * n + b0, m, dev)
-        odd = (torch.arange(m, device=dev) % 2 == 1)
-        a[odd] = c3[odd]
-        raw[b0:b0 + m] = a
+
+    def gen(first, count):
+        out = torch.empty((count, BLOCK), dtype=torch.uint8, device=dev)
+        for b0 in range(0, count, 8192):
+            m = min(8192, count - b0)
+            a = make_blocks(torch, corpus_dev, first + b0, m, dev)
+            c3 = make_blocks_config3(torch, first + b0, m, dev)
+            odd = (torch.arange(m, device=dev) % 2 == 1)
+            a[odd] = c3[odd]
+            out[b0:b0 + m] = a
+        return out
+
+    raw = gen(rank * n, n)
     gw = torch.Generator(device=dev)
     gw.manual_seed(12345)
     weights = torch.randint(-(2**62), 2**62, (BLOCK // 8,), device=dev, generator=gw, dtype=torch.int64) | 1
@@ -466,8 +633,8 @@ def run_roundtrip(args, torch, dist, engine, world, rank, local, dev):
     st2 = torch.zeros(n, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
-    def step():
-        engine.compress_batch_device(raw.view(-1), r_off, r_len, slots, s_off, s_cap, s_len, st1, 0, stream)
+    def step(src=None):
+        engine.compress_batch_device(raw.view(-1) if src is None else src, r_off, r_len, slots, s_off, s_cap, s_len, st1, 0, stream)
         engine.decompress_batch_device(slots, s_off, s_len, back, r_off, r_len, o_len, st2, stream)
 
     def barrier():
@@ -488,6 +655,7 @@ def run_roundtrip(args, torch, dist, engine, world, rank, local, dev):
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    launches = engine.launch_count - launches0
     assert int(st1.abs().sum()) == 0 and int(st2.abs().sum()) == 0
     assert torch.equal(block_checksums(torch, back, weights), sums), "round trip differs from the source"
     cbytes = float(s_len.to(torch.int64).sum())
@@ -497,38 +665,83 @@ def run_roundtrip(args, torch, dist, engine, world, rank, local, dev):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        # scatter raw blocks from rank 0 / gather compressed blocks back, on a sample of 2^13 blocks per rank
+        # ---- root-sourced: the whole corpus (world x n blocks) starts and ends on rank 0 ----
         from snappier_b200 import sharding as SH
-        ns = min(n, 1 << 13)
-        tot = ns * world
+        del raw
+        torch.cuda.empty_cache()
+        tot = n * world
         if rank == 0:
-            src = raw[:ns].repeat(world, 1).view(-1)
+            src = gen(0, tot).view(-1)
+            all_sums = block_checksums(torch, src, weights)
             soff = torch.arange(tot, device=dev, dtype=torch.int64) * BLOCK
             slen = torch.full((tot,), BLOCK, dtype=torch.int32, device=dev)
         else:
             src = soff = slen = None
-        for it in range(2):  # the first pass pays NCCL's lazy peer-to-peer connection setup: time the second
+        ph = {}
+        for it in range(2):  # the first pass pays NCCL's lazy peer-to-peer connection setup: the second is reported
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             barrier()
-            t0 = time.perf_counter()
-            SH.scatter_batch(src, soff, slen, 0, dev)
+            ev[0].record()
+            my_base, my_off, my_len, first, _ = SH.scatter_batch(src, soff, slen, 0, dev)
+            ev[1].record()
+            engine.compress_batch_device(my_base, my_off, my_len, slots, s_off, s_cap, s_len, st1, 0, stream)
+            ev[2].record()
+            engine.decompress_batch_device(slots, s_off, s_len, back, r_off, r_len, o_len, st2, stream)
+            ev[3].record()
+            g_base, g_off, g_len = SH.gather_batch(slots, s_off, s_len, 0, engine=engine)
+            ev[4].record()
             barrier()
-            t1 = time.perf_counter()
-            SH.gather_batch(slots, s_off[:ns], s_len[:ns], 0)
-            barrier()
-            t2 = time.perf_counter()
-        link = {"sample_blocks_per_rank": ns, "scatter_raw_GBps": round(tot * BLOCK / (t1 - t0) / 1e9, 1),
-                "gather_compressed_GBps": round(float(s_len[:ns].to(torch.int64).sum()) * world / (t2 - t1) / 1e9, 1)}
+            ph = torch.tensor([ev[i].elapsed_time(ev[i + 1]) for i in range(4)], dtype=torch.float64, device=dev)
+            dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+            # every rank's decompressed shard equals the slice of the corpus it was sent
+            assert int(st1.abs().sum()) == 0 and int(st2.abs().sum()) == 0
+            assert torch.equal(back[: my_base.numel()], my_base[: back.numel()]), "root-sourced round trip differs"
+            del my_base
+        sc_ms, c_ms, d_ms, g_ms = [float(x) for x in ph]
+        if rank == 0:
+            # the gathered batch decodes to the corpus: checksum a sample of it (first blocks of every rank's range)
+            gl = g_len.to(torch.int64)
+            g_bytes = int(gl.sum())
+            ns = min(n, 4096)
+            for r in range(world):
+                sel = slice(r * n, r * n + ns)
+                tmp = torch.empty(ns * BLOCK, dtype=torch.uint8, device=dev)
+                engine.decompress_batch_device(g_base, g_off[sel].contiguous(), g_len[sel].contiguous(), tmp, r_off[:ns], r_len[:ns],
+                                               o_len[:ns], st2[:ns], stream)
+                torch.cuda.synchronize()
+                assert int(st2[:ns].abs().sum()) == 0 and torch.equal(block_checksums(torch, tmp, weights), all_sums[sel])
+            total_ms = sc_ms + c_ms + d_ms + g_ms
+            link = {"blocks_per_rank": n, "corpus_bytes": int(tot) * BLOCK,
+                    "scatter_raw_GBps": round(tot * BLOCK / sc_ms / 1e6, 1),
+                    "gather_compressed_GBps": round(g_bytes / g_ms / 1e6, 1),
+                    "scatter_ms": round(sc_ms, 2), "compress_ms": round(c_ms, 2), "decompress_ms": round(d_ms, 2),
+                    "gather_ms": round(g_ms, 2),
+                    "root_sourced_roundtrip_GBps": round(tot * BLOCK / total_ms / 1e6, 1),
+                    "bound": f"rank 0's NVLink: it sends {world - 1}/{world} of the raw corpus and receives {world - 1}/{world} "
+                             "of the compressed corpus (770 GB/s per direction measured, 900 nominal)",
+                    "collectives": "1 broadcast (byte counts) + 1 grouped send/recv (scatter); 1 all_gather (counts) + "
+                                   "1 grouped send/recv (gather); snp_pack_batch packs the slots before the send"}
+    if rank != 0:
+        return None
+    ms = float(t[0])
+    u, c = float(b[0]), float(b[1])
+    return {
+        "metric": "uncompressed GB/s (compress + decompress round trip, 64 KiB blocks)", "value": round(u / ms / 1e6, 2),
+        "unit": "GB/s", "ms_per_step": round(ms, 3),
+        "config": {"workload": f"round trip: {n} mixed 64 KiB blocks per GPU (config-2 mixture and config-3 blocks 1:1), "
+                               "born sharded by contiguous block range, compress then decompress, checksum-verified",
+                   "ratio": round(c / u, 4), "hash_mode": "crc32c", "parallelism": f"block-range shard x{world}"},
+        "nccl_scatter_gather": link, "gpu_launches": int(launches), "clocks": clk.summary()}
+
+
+def run_roundtrip(args, torch, dist, engine, world, rank, local, dev):
+    """--workload roundtrip: config 5 as a line of its own."""
+    sec = roundtrip_section(args, torch, dist, engine, world, rank, local, dev)
     if rank == 0:
-        ms = float(t[0])
-        u, c = float(b[0]), float(b[1])
-        print(json.dumps({
-            "metric": "uncompressed GB/s (compress + decompress round trip, 64 KiB blocks)", "value": round(u / ms / 1e6, 2),
-            "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"round trip: {n} mixed 64 KiB blocks per GPU (config-2 mixture and config-3 blocks 1:1), "
-                                   "born sharded by contiguous block range, compress then decompress, checksum-verified",
-                       "ratio": round(c / u, 4), "hash_mode": "crc32c", "parallelism": f"block-range shard x{world}"},
-            "nccl_scatter_gather": link, "gpu_launches": int(engine.launch_count - launches0), "clocks": clk.summary()}))
+        line = {"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic"}
+        line.update(sec)
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -543,10 +756,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blocks", type=int, default=1 << 20, help="blocks per GPU (default 2^20 = BASELINE config 2)")
     ap.add_argument("--e2e-blocks", type=int, default=1 << 15)
-    ap.add_argument("--cpu-blocks", type=int, default=1 << 13)
+    ap.add_argument("--cpu-blocks", type=int, default=1 << 16)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--ref-blocks", type=int, default=1 << 13)
+    ap.add_argument("--ref-blocks", type=int, default=1 << 16)
+    ap.add_argument("--ref-compress-blocks", type=int, default=1 << 15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decompress-only", action="store_true", help="skip the compress (and, for N > 1, round-trip) sections")
     ap.add_argument("--workload", default="decompress", choices=["decompress", "compress", "frame", "roundtrip"],
                     help="decompress = BASELINE config 2 (the headline); compress = config 3, frame = config 4, "
                          "roundtrip = config 5 (extra lines, not the driver's)")
@@ -651,63 +866,70 @@ def main():
     e2e_val = world * ne * BLOCK / float(te[0]) / 1e9
     meta_bytes = ne * (8 + 8 + 4 + 4)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     # ---- roofline of the (single) dominant kernel --------------------------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    k_ms = float(np.mean(kernel_ms))
-    alg_bytes = (float(n) * BLOCK + float(comp_bytes))  # rank 0's launch: C_i read + U_i written
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        per_block = json.load(open(tpath)).get("decompress_dram_bytes_per_block")
+    line = None
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        k_ms = float(np.mean(kernel_ms))
+        alg_bytes = (float(n) * BLOCK + float(comp_bytes))  # rank 0's launch: C_i read + U_i written
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        per_block, tsrc = traffic_per_block("decompress_dram_bytes_per_block")
         traffic = int(per_block * n) if per_block else None  # ncu --set full capture, scaled to this launch
 
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:  # the host-core baseline is reported by the single-GPU run only
-        nc = min(args.cpu_blocks, n)
-        cb = int(c_off[nc - 1] + c_len[nc - 1])
-        threads = os.cpu_count() or 1
-        v, passes, dt = cpu_reference_run(comp[:cb].cpu().numpy(), c_off[:nc].cpu().numpy().astype(np.uint64),
-                                          c_len[:nc].cpu().numpy().astype(np.uint32), threads, args.cpu_seconds)
-        h_comp = comp[:cb].cpu().numpy()
-        h_off = c_off[:nc].cpu().numpy().astype(np.uint64)
-        h_len = c_len[:nc].cpu().numpy().astype(np.uint32)
-        dn = dotnet_probe()
-        cpu = {"value": round(v, 3), "unit": "GB/s", "cores": threads, "kind": "port",
-               "sample": f"first {nc} blocks of rank 0's batch, {passes} passes in {dt:.1f} s, oracle C port of the "
-                         f"reference algorithm (Snappier's C# cannot run here: " +
-                         (f"dotnet {dn} found, see csharp/Bench)" if dn else "no .NET SDK)"),
-               "google_snappy_1thread_GBps": sanity_anchor(h_comp, h_off, h_len), "dotnet": dn}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:  # the host-core baseline is reported by the single-GPU run only
+            nc = min(args.cpu_blocks, n)
+            cb = int(c_off[nc - 1] + c_len[nc - 1])
+            threads = os.cpu_count() or 1
+            h_comp = comp[:cb].cpu().numpy()
+            h_off = c_off[:nc].cpu().numpy().astype(np.uint64)
+            h_len = c_len[:nc].cpu().numpy().astype(np.uint32)
+            v, passes, dt = cpu_reference_run(h_comp, h_off, h_len, threads, args.cpu_seconds)
+            dn = dotnet_probe()
+            cpu = {"value": round(v, 3), "unit": "GB/s", "cores": threads, "kind": "port",
+                   "sample": f"first {nc} blocks of rank 0's batch, {passes} passes in {dt:.1f} s, oracle C port of the "
+                             f"reference algorithm (Snappier's C# cannot run here: " +
+                             (f"dotnet {dn} found, see csharp/Bench)" if dn else "no .NET SDK)"),
+                   "google_snappy_1thread_GBps": sanity_anchor(h_comp, h_off, h_len), "dotnet": dn}
+            del h_comp
 
-    print(json.dumps({
-        "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD if n == (1 << 20) else WORKLOAD.replace("2^20", str(n)),
-                   "blocks_per_gpu": n, "block_bytes": BLOCK, "compressed_bytes_per_gpu": int(comp_bytes),
-                   "ratio": round(c_bytes / u_bytes, 4), "hash_mode": "crc32c", "parallelism": f"block-range shard x{world}",
-                   "l2": "inputs+outputs per step far exceed the 126 MB L2 (no flush needed)" if n * BLOCK > (1 << 30)
-                         else "WARNING: working set is small relative to L2"},
-        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "snp::k_decompress", "kernel_ms": round(k_ms, 4),
-                     "algorithmic_bytes_per_launch": int(alg_bytes)},
-        "cpu_baseline": cpu,
-        "e2e": {"value": round(e2e_val, 3), "unit": "GB/s", "h2d_bytes_per_step": int(e_bytes + meta_bytes),
-                "d2h_bytes_per_step": int(ne * BLOCK + ne * 8), "blocks_per_step": ne,
-                "path": "snp_decompress_batch(SNP_MEM_HOST) on pinned host buffers"},
-        "gpu_launches": int(launches),
-        "clocks": clk.summary(),
-    }))
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD if n == (1 << 20) else WORKLOAD.replace("2^20", str(n)),
+                       "blocks_per_gpu": n, "block_bytes": BLOCK, "compressed_bytes_per_gpu": int(comp_bytes),
+                       "ratio": round(c_bytes / u_bytes, 4), "hash_mode": "crc32c", "parallelism": f"block-range shard x{world}",
+                       "l2": "inputs+outputs per step far exceed the 126 MB L2 (no flush needed)" if n * BLOCK > (1 << 30)
+                             else "WARNING: working set is small relative to L2"},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
+                         "kernel": DECOMPRESS_KERNEL, "kernel_ms": round(k_ms, 4),
+                         "algorithmic_bytes_per_launch": int(alg_bytes)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": round(e2e_val, 3), "unit": "GB/s", "h2d_bytes_per_step": int(e_bytes + meta_bytes),
+                    "d2h_bytes_per_step": int(ne * BLOCK + ne * 8), "blocks_per_step": ne,
+                    "path": "snp_decompress_batch(SNP_MEM_HOST) on pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+        }
+
+    # ---- the other half of BASELINE's metric (config 3) and, across GPUs, config 5: same JSON line ----
+    del comp, out, h_in, h_out, np_in, np_out
+    torch.cuda.empty_cache()
+    if not args.decompress_only:
+        sec = compress_section(args, torch, dist, engine, world, rank, local, dev)
+        if rank == 0:
+            line["compress"] = sec
+            line["gpu_launches"] += sec["gpu_launches"]
+        torch.cuda.empty_cache()
+        if world > 1:
+            rt = roundtrip_section(args, torch, dist, engine, world, rank, local, dev)
+            if rank == 0:
+                line["roundtrip"] = rt
+                line["nccl_scatter_gather"] = rt["nccl_scatter_gather"]
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

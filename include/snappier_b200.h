@@ -179,6 +179,15 @@ int snp_frame_uncompressed_length(const uint8_t *in, size_t n, uint64_t *len);
  * status is that of the first bad chunk in stream order. */
 int snp_frame_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written);
 
+/* Packs a batch: copies item i's len[i] bytes from src_base + src_off[i] to dst_base + dst_off[i], where dst_off is the
+ * exclusive prefix sum of len (written by the call) and *total their sum -- the batched form of what
+ * Snappy.CompressToMemory returns per call (Snappy.cs:84-100: exactly the compressed bytes, no slack), and the gather(v)
+ * side of block-range sharding (SnappyCompressor.cs:40-44: blocks are independent).  DEVICE pointers only (src/dst/len/
+ * dst_off/total); enqueued on `stream`, asynchronous.  dst_base == NULL: offsets and total only (size query).
+ * dst must not overlap src.  Calls on one context that run concurrently on different streams must not overlap in time. */
+int snp_pack_batch(snp_ctx *ctx, const uint8_t *src_base, const uint64_t *src_off, const uint32_t *len, size_t n_items,
+                   uint8_t *dst_base, uint64_t *dst_off, uint64_t *total, void *stream);
+
 /* Batched Crc32CAlgorithm.Compute (+ ApplyMask when masked != 0), Crc32CAlgorithm.cs:41-44,157-158. */
 int snp_crc32c_batch(snp_ctx *ctx, const uint8_t *base, const uint64_t *off, const uint32_t *len,
                      uint32_t *crc, size_t n_items, int masked, int mem_kind, void *stream);

@@ -86,6 +86,20 @@ class Engine:
             self._check_dev(status, 4, "status"), n, N.MEM_DEVICE, stream)
         N.check_call(rc, "snp_uncompressed_length_batch")
 
+    def pack_batch_device(self, src_base, src_off, length, dst_base=None, stream: int | None = None):
+        """Dense packing of a batch (slots with slack -> exactly the items' bytes, in order).  Returns (dst_off i64[N],
+        total i64[1]) on the device; with dst_base=None only the offsets / total are computed (size query)."""
+        import torch
+        n = src_off.numel()
+        dst_off = torch.empty(n, dtype=torch.int64, device=src_off.device)
+        total = torch.zeros(1, dtype=torch.int64, device=src_off.device)
+        rc = N.lib().snp_pack_batch(
+            self._ctx, self._check_dev(src_base, 1, "src_base"), self._check_dev(src_off, 8, "src_off"),
+            self._check_dev(length, 4, "length"), n, None if dst_base is None else self._check_dev(dst_base, 1, "dst_base"),
+            dst_off.data_ptr(), total.data_ptr(), stream)
+        N.check_call(rc, "snp_pack_batch")
+        return dst_off, total
+
     # --------------------------------------------------------------- host mode
     def compress_batch_host(self, in_base: np.ndarray, in_off, in_len, out_base: np.ndarray, out_off,
                             out_cap, hash_mode: int = N.HASH_CRC32C):

@@ -82,7 +82,7 @@ __device__ __forceinline__ uint32_t adv4_v7(uint32_t w) {
 // Cooperative copy of a long literal, input -> output, as 16-byte vectors aligned on the destination.
 __device__ __forceinline__ void copy_literal_wide7(const uint8_t *__restrict__ s, uint8_t *d, uint32_t len,
                                                    const uint8_t *in_end, unsigned lane) {
-    const uint32_t h = (uint32_t)(-(intptr_t)d) & 15u;  // bytes up to the first 16-byte boundary of d
+    const uint32_t h = min((uint32_t)(-(intptr_t)d) & 15u, len);  // bytes up to the first 16-byte boundary of d
     if (lane < h) d[lane] = s[lane];
     const uint8_t *sv = s + h;
     uint4 *dv = reinterpret_cast<uint4 *>(d + h);

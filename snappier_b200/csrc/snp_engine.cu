@@ -397,6 +397,101 @@ __global__ void k_frag_gather(const uint8_t *__restrict__ tmp, size_t pitch, con
     }
 }
 
+// ---- packing a batch: slots with slack -> dense bytes (the gather(v) side of block-range sharding, SURVEY.md 8(e);
+// the batched form of what Snappy.CompressToMemory returns: exactly the compressed bytes, no slack) --------------------
+// Exclusive scan of len[0..n) in three launches: per-CTA sums, scan of the sums (one CTA), per-CTA offsets.
+constexpr int kScanItems = 2048;  // items per CTA (256 threads x 8)
+
+__global__ void __launch_bounds__(256) k_pack_sums(const uint32_t *__restrict__ len, uint64_t *__restrict__ part, size_t n) {
+    __shared__ uint64_t ws[8];
+    const size_t base = (size_t)blockIdx.x * kScanItems;
+    uint64_t sum = 0;
+    for (int k = 0; k < 8; k++) {
+        const size_t i = base + (size_t)k * 256 + threadIdx.x;
+        if (i < n) sum += len[i];
+    }
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(SNP_FULL, sum, d);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = 0;
+        for (int w = 0; w < 8; w++) t += ws[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_pack_scan_sums(uint64_t *__restrict__ part, size_t nparts, uint64_t *__restrict__ total) {
+    __shared__ uint64_t ws[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t b0 = 0; b0 < nparts; b0 += 1024) {
+        const size_t i = b0 + threadIdx.x;
+        const uint64_t v = i < nparts ? part[i] : 0;
+        uint64_t inc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t y = __shfl_up_sync(SNP_FULL, inc, d);
+            if ((threadIdx.x & 31) >= (unsigned)d) inc += y;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t w = ws[threadIdx.x], winc = w;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t y = __shfl_up_sync(SNP_FULL, winc, d);
+                if (threadIdx.x >= (unsigned)d) winc += y;
+            }
+            ws[threadIdx.x] = winc - w;  // exclusive over the warps
+        }
+        __syncthreads();
+        const uint64_t excl = carry + ws[threadIdx.x >> 5] + inc - v;
+        if (i < nparts) part[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(256) k_pack_offsets(const uint32_t *__restrict__ len, const uint64_t *__restrict__ part,
+                                                      uint64_t *__restrict__ off, size_t n) {
+    __shared__ uint64_t ws[8];
+    const size_t i0 = (size_t)blockIdx.x * kScanItems + (size_t)threadIdx.x * 8;
+    uint32_t l[8];
+    uint64_t sum = 0;
+    for (int k = 0; k < 8; k++) {
+        l[k] = i0 + k < n ? len[i0 + k] : 0u;
+        sum += l[k];
+    }
+    uint64_t inc = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t y = __shfl_up_sync(SNP_FULL, inc, d);
+        if ((threadIdx.x & 31) >= (unsigned)d) inc += y;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    uint64_t run = part[blockIdx.x] + inc - sum;
+    for (unsigned w = 0; w < (threadIdx.x >> 5); w++) run += ws[w];
+    for (int k = 0; k < 8; k++) {
+        if (i0 + k < n) off[i0 + k] = run;
+        run += l[k];
+    }
+}
+
+// One warp per item, 16-byte vectors aligned on the destination (the sources are slots, usually 16-byte aligned).
+__global__ void __launch_bounds__(256) k_pack_copy(const uint8_t *__restrict__ src_base, const uint64_t *__restrict__ src_off,
+                                                   const uint32_t *__restrict__ len, uint8_t *__restrict__ dst_base,
+                                                   const uint64_t *__restrict__ dst_off, size_t n) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (size_t i = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+        const uint32_t l = len[i];
+        if (l == 0) continue;
+        const uint8_t *sp = src_base + src_off[i];
+        snp::copy_literal_wide7(sp, dst_base + dst_off[i], l, sp + l, lane);
+    }
+}
+
 // --------------------------------------------------------- host-mode staging --
 
 struct Span {
@@ -1036,6 +1131,34 @@ int snp_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t
 // ------------------------------------------------------------- framing format --
 
 size_t snp_frame_max_compressed_length(size_t n) { return 10 + n + 8 * ((n + SNP_BLOCK_SIZE - 1) / SNP_BLOCK_SIZE); }
+
+int snp_pack_batch(snp_ctx *c, const uint8_t *src_base, const uint64_t *src_off, const uint32_t *len, size_t n,
+                   uint8_t *dst_base, uint64_t *dst_off, uint64_t *total, void *stream) {
+    if (!c || (n && (!src_base || !src_off || !len || !dst_off)) || !total) return SNP_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        CU(cudaMemsetAsync(total, 0, 8, s));
+        return SNP_OK;
+    }
+    const size_t nparts = (n + kScanItems - 1) / kScanItems;
+    // the partial sums live in the context's scratch: launches on different streams are chained like the compress tables
+    int rc;
+    if ((rc = c->d_tmp.reserve(nparts * 8))) return rc;
+    uint64_t *part = (uint64_t *)c->d_tmp.p;
+    k_pack_sums<<<(unsigned)nparts, 256, 0, s>>>(len, part, n);
+    k_pack_scan_sums<<<1, 1024, 0, s>>>(part, nparts, total);
+    k_pack_offsets<<<(unsigned)nparts, 256, 0, s>>>(len, part, dst_off, n);
+    if (dst_base) {
+        const unsigned grid = (unsigned)std::min((n + 7) / 8, (size_t)c->sm_count * 8);
+        k_pack_copy<<<grid, 256, 0, s>>>(src_base, src_off, len, dst_base, dst_off, n);
+        c->launches++;
+    }
+    c->launches += 3;
+    CU(cudaGetLastError());
+    return SNP_OK;
+}
 
 int snp_crc32c_batch(snp_ctx *c, const uint8_t *base, const uint64_t *off, const uint32_t *len, uint32_t *crc,
                      size_t n, int masked, int mem_kind, void *stream) {

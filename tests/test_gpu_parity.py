@@ -542,3 +542,33 @@ def test_argument_errors(engine):
     out_len, status = engine.compress_batch_host(base, off, ln, out, np.arange(3, dtype=np.uint64) * 80000,
                                                  np.full(3, 80000, np.uint32))
     assert status[0] == 0 and status[2] == 0 and status[1] == N.E_INVALID_ARG and out_len[1] == 0
+
+
+def test_pack_batch_matches_concatenation(engine):
+    """snp_pack_batch: slots with slack -> the items' bytes back to back (what a caller of Snappy.CompressToMemory gets
+    per block), offsets = exclusive prefix sum, for ragged lengths (zero-length items, lengths around the 16-byte vector
+    width, misaligned sources) and for more items than one scan CTA covers."""
+    import torch
+    rng = np.random.default_rng(21)
+    dev = torch.device("cuda", 0)
+    for n, maxlen in ((1, 100), (7, 40), (5000, 700), (70000, 90)):
+        lens = rng.integers(0, maxlen, size=n).astype(np.int32)
+        lens[rng.integers(0, n, size=max(1, n // 10))] = 0
+        slack = rng.integers(0, 37, size=n).astype(np.int64)
+        src_off = np.cumsum(lens.astype(np.int64) + slack) - lens  # item i sits behind its slack
+        total_src = int(src_off[-1] + lens[-1]) + 64
+        src = rng.integers(0, 256, size=total_src, dtype=np.uint8)
+        want = b"".join(src[o:o + l].tobytes() for o, l in zip(src_off, lens))
+        t_src = torch.from_numpy(src).to(dev)
+        t_off = torch.from_numpy(src_off).to(dev)
+        t_len = torch.from_numpy(lens).to(dev)
+        off_q, tot_q = engine.pack_batch_device(t_src, t_off, t_len, None)
+        assert int(tot_q) == len(want)
+        dst = torch.full((len(want) + 32,), 0xEE, dtype=torch.uint8, device=dev)
+        off, tot = engine.pack_batch_device(t_src, t_off, t_len, dst[16:])
+        torch.cuda.synchronize()
+        assert int(tot) == len(want)
+        assert np.array_equal(off.cpu().numpy(), np.cumsum(lens.astype(np.int64)) - lens)
+        got = dst.cpu().numpy()
+        assert got[16:16 + len(want)].tobytes() == want
+        assert (got[:16] == 0xEE).all() and (got[16 + len(want):] == 0xEE).all()
