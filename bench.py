@@ -678,7 +678,9 @@ def roundtrip_section(args, torch, dist, engine, world, rank, local, dev):
         else:
             src = soff = slen = None
         ph = {}
+        g_base = g_off = g_len = None
         for it in range(2):  # the first pass pays NCCL's lazy peer-to-peer connection setup: the second is reported
+            g_base = g_off = g_len = None  # the caching allocator hands the first pass's buffers to the second
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             barrier()
             ev[0].record()

@@ -128,6 +128,8 @@ struct snp_ctx {
         cudaStream_t stream = nullptr;
         cudaEvent_t meta_ready = nullptr;
         DevBuf d_in, d_out, d_meta;
+        DevBuf d_tables;   // hash tables of this slot's compress launches (sized by the chunk's grid): the chunks of the
+                           // host-mode pipeline compress concurrently, each on its slot's stream
         PinnedBuf h_meta;  // same layout as d_meta: async both ways regardless of the caller's arrays
     } slots[kSlots];
     bool attrs_set = false;
@@ -263,15 +265,18 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
 
 int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const uint64_t *in_off,
                     const uint32_t *in_len, uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap,
-                    uint32_t *out_len, int32_t *status, size_t n, uint32_t hash_mode, int frag_mode) {
+                    uint32_t *out_len, int32_t *status, size_t n, uint32_t hash_mode, int frag_mode,
+                    DevBuf *own_tables = nullptr) {
     if (n == 0) return SNP_OK;
     int rc = ctx_set_attrs(c);
     if (rc) return rc;
+    // own_tables: a table buffer that only launches on stream s use (a pipeline slot): no cross-stream ordering needed
+    DevBuf &tables = own_tables ? *own_tables : c->d_tables;
     // The L2-table kernels share ONE table buffer (a slice per resident CTA/warp), and the host-mode pipeline launches
     // consecutive chunks on different streams: a chunk's CTAs could start in the tail of the previous launch and clear a
     // slice that one of its warps is still using.  Launches on different streams are therefore chained with an event
     // (each launch fills the GPU by itself, so nothing is lost; the copies of the chunks still overlap).
-    const bool shared_tables = c->comp_kernel >= 3;
+    const bool shared_tables = c->comp_kernel >= 3 && !own_tables;
     if (shared_tables) {
         if (!c->tables_done) CU(cudaEventCreateWithFlags(&c->tables_done, cudaEventDisableTiming));
         if (c->tables_used && c->tables_last_stream != s) CU(cudaStreamWaitEvent(s, c->tables_done, 0));
@@ -294,14 +299,14 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
         const int cps = c->comp_ctas_per_sm;
         const size_t ctas5 = (n + gpc - 1) / gpc;
         const unsigned grid5 = (unsigned)std::min(ctas5, (size_t)c->sm_count * cps);
-        if ((rc = c->d_tables.reserve((size_t)c->sm_count * cps * gpc * 65536))) return rc;
+        if ((rc = tables.reserve((size_t)grid5 * gpc * 65536))) return rc;
         const int fm = frag_mode | (c->comp_first_width << 8);
         if (hash_mode == SNP_HASH_CRC32C)
             snp::k_compress_v5<SNP_HASH_CRC32C, W><<<grid5, 256, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap,
-                                                                        out_len, status, n, fm, ctr, (uint32_t *)c->d_tables.p);
+                                                                        out_len, status, n, fm, ctr, (uint32_t *)tables.p);
         else
             snp::k_compress_v5<SNP_HASH_MUL, W><<<grid5, 256, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap,
-                                                                     out_len, status, n, fm, ctr, (uint32_t *)c->d_tables.p);
+                                                                     out_len, status, n, fm, ctr, (uint32_t *)tables.p);
     } else if (c->comp_kernel >= 3) {
         // hash tables in global memory (L2): occupancy no longer capped by shared memory
         unsigned long long *ctr;
@@ -310,13 +315,13 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
         const int cps = c->comp_ctas_per_sm;
         size_t ctas3 = (n + wpc - 1) / wpc;
         unsigned grid3 = (unsigned)std::min(ctas3, (size_t)c->sm_count * cps);
-        const size_t table_bytes = (size_t)c->sm_count * cps * wpc * 65536;
-        if ((rc = c->d_tables.reserve(table_bytes))) return rc;
+        const size_t table_bytes = (size_t)grid3 * wpc * 65536;  // one 64 KiB slice per warp of THIS launch
+        if ((rc = tables.reserve(table_bytes))) return rc;
 #define SNP_LAUNCH_C3(H, V)                                                                                  \
     snp::k_compress_v3<H, V><<<grid3, wpc * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap, \
                                                               out_len, status, n,                                  \
                                                               frag_mode | (c->comp_first_width << 8), ctr,         \
-                                                              (uint32_t *)c->d_tables.p)
+                                                              (uint32_t *)tables.p)
         if (c->comp_kernel == 3) {
             if (hash_mode == SNP_HASH_CRC32C) SNP_LAUNCH_C3(SNP_HASH_CRC32C, 3);
             else SNP_LAUNCH_C3(SNP_HASH_MUL, 3);
@@ -523,6 +528,7 @@ struct Chunk {
     Span si, so;
     int slot = 0;
     bool early_d2h = false;  // the payload copy was already enqueued in phase 1
+    int trace_idx = -1;
 };
 
 int chunk_phase1(snp_ctx *c, Chunk &ck, bool compress, const uint8_t *in_base, const uint64_t *in_off,
@@ -565,7 +571,7 @@ int chunk_phase1(snp_ctx *c, Chunk &ck, bool compress, const uint8_t *in_base, c
     auto *d_status = (int32_t *)(dm + ml.status);
     if (compress)
         rc = launch_compress(c, s, (const uint8_t *)sl.d_in.p, d_in_off, d_in_len, (uint8_t *)sl.d_out.p, d_out_off,
-                             d_out_cap, d_out_len, d_status, n, hash_mode, 0);
+                             d_out_cap, d_out_len, d_status, n, hash_mode, 0, &sl.d_tables);
     else
         rc = launch_decompress(c, s, (const uint8_t *)sl.d_in.p, d_in_off, d_in_len, (uint8_t *)sl.d_out.p,
                                d_out_off, d_out_cap, d_out_len, d_status, n);
@@ -588,7 +594,10 @@ int chunk_phase1(snp_ctx *c, Chunk &ck, bool compress, const uint8_t *in_base, c
             ck.early_d2h = true;
         }
     }
-    if (c->host_trace) c->trace.push_back({tev[0], tev[1], tev[2], tev[3], tev[4]});
+    if (c->host_trace) {
+        ck.trace_idx = (int)c->trace.size();
+        c->trace.push_back({tev[0], tev[1], tev[2], tev[3], tev[4]});
+    }
     return SNP_OK;
 }
 
@@ -605,8 +614,38 @@ int chunk_phase2(snp_ctx *c, const Chunk &ck, uint8_t *out_base, const uint64_t 
         memcpy(status + ck.a, hm + ml.status, (ck.b - ck.a) * 4);
     }
     if (ck.early_d2h) return SNP_OK;
+    const bool tr = c->host_trace && ck.trace_idx >= 0;
+    if (tr) CU(cudaEventRecord(c->trace[ck.trace_idx].e[3], sl.stream));
+    struct TraceEnd {  // records the end of the payload copies on every exit path
+        snp_ctx *c; const Chunk &ck; cudaStream_t s; bool on;
+        ~TraceEnd() { if (on) cudaEventRecord(c->trace[ck.trace_idx].e[4], s); }
+    } trace_end{c, ck, sl.stream, tr};
     size_t i = ck.a;
     while (i < ck.b) {
+        // Equally spaced regions with slack behind the produced bytes (compress slots): one strided copy per group of
+        // items, as wide as the group's longest item -- the slack (more than half of a 76 496-byte slot at ratio 0.5)
+        // stays off PCIe.  A group grows while the bytes it copies beyond the items' lengths stay below 25 %.  Bytes of
+        // a region between out_len and that width are unspecified (device scratch).
+        if (i + 1 < ck.b && out_off[i + 1] > out_off[i] + out_len[i]) {
+            const uint64_t pitch = out_off[i + 1] - out_off[i];
+            size_t j = i;
+            uint64_t sum = out_len[i];
+            uint32_t width = out_len[i], cap_min = out_cap[i];
+            while (j + 1 < ck.b && out_off[j + 1] - out_off[j] == pitch) {
+                const uint32_t w2 = std::max(width, out_len[j + 1]);
+                const uint64_t s2 = sum + out_len[j + 1];
+                if ((uint64_t)w2 * (j + 2 - i) > s2 + s2 / 4 + 65536) break;
+                width = w2, sum = s2, cap_min = std::min(cap_min, out_cap[j + 1]);
+                j++;
+            }
+            if (j > i && pitch >= width && cap_min >= width) {
+                if (width)
+                    CU(cudaMemcpy2DAsync(out_base + out_off[i], pitch, (const uint8_t *)sl.d_out.p + (out_off[i] - ck.so.lo), pitch,
+                                         width, j - i + 1, cudaMemcpyDeviceToHost, sl.stream));
+                i = j + 1;
+                continue;
+            }
+        }
         size_t j = i;
         while (j + 1 < ck.b && out_off[j + 1] == out_off[j] + out_cap[j]) j++;
         uint64_t lo = out_off[i], hi = out_off[j] + out_len[j];
@@ -674,7 +713,10 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
         for (size_t i = 0; i < c->trace.size(); i++) {
             float v[5] = {};
             for (int j = 0; j < 5; j++)
-                if (c->trace[i].e[j]) cudaEventElapsedTime(&v[j], t0, c->trace[i].e[j]);
+                if (c->trace[i].e[j] && cudaEventElapsedTime(&v[j], t0, c->trace[i].e[j]) != cudaSuccess) {
+                    v[j] = 0;
+                    cudaGetLastError();  // an event that was never recorded (no payload copy): not an error of the call
+                }
             fprintf(stderr, "chunk %3zu  h2d %7.3f..%7.3f  kernel ..%7.3f  d2h %7.3f..%7.3f\n", i, v[0], v[1], v[2], v[3], v[4]);
         }
         for (auto &r : c->trace)

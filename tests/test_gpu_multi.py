@@ -56,7 +56,7 @@ eng.decompress_batch_device(slots, s_off, s_len, out, my_off, my_len, o_len, st2
 torch.cuda.synchronize()
 assert int(st.abs().sum()) == 0 and int(st2.abs().sum()) == 0
 assert torch.equal(out[: n * 65536], my_base[: n * 65536])          # round trip on this rank's shard
-g_base, g_off, g_len = sharding.gather_batch(slots, s_off, s_len, dst=0)
+g_base, g_off, g_len = sharding.gather_batch(slots, s_off, s_len, dst=0, engine=eng)   # slots packed by snp_pack_batch
 if rank == 0:
     from oracle import pyoracle as O
     gb = g_base.cpu().numpy(); go = g_off.cpu().numpy(); gl = g_len.cpu().numpy()
