@@ -589,7 +589,7 @@ def run_frame(args, torch, engine, rank, local, dev):
         "frame_compress_GBps": round(cg, 3), "frame_decompress_GBps": round(dg, 3),
         "e2e": {"value": round(2 / (1 / cg + 1 / dg), 3), "unit": "GB/s", "h2d_bytes_per_step": int(raw.numel() + nbytes),
                 "d2h_bytes_per_step": int(raw.numel() + nbytes)},
-        "gpu_launches": "n/a (thread-local default context)" if engine.launch_count == launches0 else int(engine.launch_count - launches0),
+        "gpu_launches": "n/a (the library's default context)" if engine.launch_count == launches0 else int(engine.launch_count - launches0),
         "clocks": clk.summary()}))
 
 

@@ -23,7 +23,7 @@ namespace Snappier.Internal
         {
             Ok = 0, OutputTooSmall = 1, InvalidLength = 2, Incomplete = 3, InvalidCopyOffset = 4, DataTooLong = 5,
             UnknownChunkType = 6, CrcMismatch = 7,
-            CudaError = -1, InvalidArgument = -2, NoDevice = -3, Overlap = -4,
+            CudaError = -1, InvalidArgument = -2, NoDevice = -3, Overlap = -4, NoMemory = -5, Internal = -6,
         }
 
         internal enum HashMode : uint { Crc32C = 0, Mul = 1 }
@@ -157,6 +157,7 @@ namespace Snappier.Internal
                 case Status.Overlap: ThrowHelper.ThrowInvalidOperationException("Input and output spans must not overlap."); return; // SnappyCompressor.cs:29
                 case Status.UnknownChunkType: ThrowHelper.ThrowInvalidDataException("Unknown chunk type"); return;   // SnappyStreamDecompressor.cs:182-185
                 case Status.CrcMismatch: ThrowHelper.ThrowInvalidDataException("Chunk CRC mismatch."); return;       // SnappyStreamDecompressor.cs:127-131
+                case Status.NoMemory: throw new OutOfMemoryException("snappier_b200: host allocation failed");
                 default:
                     throw new InvalidOperationException(
                         $"snappier_b200: {st}: {Marshal.PtrToStringUTF8(snp_last_error())} (there is no CPU fallback)");

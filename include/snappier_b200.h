@@ -52,9 +52,11 @@ enum snp_error {
     SNP_E_CUDA = -1,        /* a CUDA call failed; see snp_last_error() */
     SNP_E_INVALID_ARG = -2, /* null pointer / bad enum / overlap */
     SNP_E_NO_DEVICE = -3,   /* no CUDA device or kernel image not loadable */
-    SNP_E_OVERLAP = -4      /* input and output overlap -> InvalidOperationException
+    SNP_E_OVERLAP = -4,     /* input and output overlap -> InvalidOperationException
                                ("Input and output spans must not overlap.",
                                SnappyCompressor.cs:27-30) */
+    SNP_E_NOMEM = -5,       /* a host allocation failed -> OutOfMemoryException */
+    SNP_E_INTERNAL = -6     /* an unexpected C++ exception was caught at the ABI boundary; see snp_last_error() */
 };
 
 /* Hash used by the compressor's match finder (HashTable.cs:91-126).  Snappier
@@ -88,8 +90,13 @@ int snp_uncompressed_length(const uint8_t *in, size_t n, uint32_t *len);
 /* ---- contexts ---------------------------------------------------------- */
 /* One context = one GPU + one private stream + reusable staging buffers.  A
  * context may be used by one thread at a time (calls on it are serialised by
- * an internal mutex).  The single-call API below uses a lazily created
- * thread-local context on the current device. */
+ * an internal mutex).  The single-call API below shares ONE lazily created
+ * process-wide context per device (the current device of the calling thread):
+ * device scratch does not grow with the number of calling threads.  Scratch
+ * follows the largest call so far: ~2.2 x the 64 MiB pipeline chunk per slot
+ * in use, plus 64 KiB of hash table per concurrently compressed 64 KiB block
+ * (512 KiB for a one-block call).  No C++ exception crosses this ABI: host
+ * allocation failures return SNP_E_NOMEM. */
 typedef struct snp_ctx snp_ctx;
 int snp_create(int device, snp_ctx **ctx);
 void snp_destroy(snp_ctx *ctx);

@@ -18,11 +18,8 @@
 
 #include "snp_common.cuh"
 #include "snp_compress_v1.cuh"
-#include "snp_compress_v2.cuh"
-#include "snp_compress_v5.cuh"
+#include "snp_compress_v3.cuh"
 #include "snp_decompress_v1.cuh"
-#include "snp_decompress_v3.cuh"
-#include "snp_decompress_v5.cuh"
 #include "snp_decompress_v7.cuh"
 #include "snp_decompress_v8.cuh"
 #include "snp_frame.cuh"
@@ -99,16 +96,14 @@ struct snp_ctx {
     std::mutex mu;
     std::atomic<uint64_t> launches{0};
     int sm_count = 148;
-    int decomp_kernel = 7;  // SNP_DECOMP_KERNEL: 7 = tag-group engine (TMA-staged input ring, advance-table walk, output
-                            // window; the default), 5 = the round-1 default (sparse-tag prefix engine + speculative
-                            // dense engine; kept as the A/B challenger), 1 = warp-uniform baseline
+    int decomp_kernel = 7;  // SNP_DECOMP_KERNEL: 7 = warp-per-block tag-group engine (TMA-staged input ring, advance-table
+                            // walk, output window; the default), 8 = lane-per-block engine (the challenger: faster on
+                            // batches of <= 4 KiB blocks), 1 = warp-uniform baseline (also the > 2 GiB path)
     int v7_window = 4096;   // SNP_V7_WINDOW: output window bytes per warp of k_decompress_v7: 4096 (32 warps per SM, the
-                            // default), 2048 (40 warps; 48 with SNP_V7_CTAS=6), 8192 (20 warps)
-    int v7_ctas = 0;        // SNP_V7_CTAS
+                            // default) or 2048 (40 warps per SM)
     int v8_cfg = 0;         // SNP_V8_CFG: lane-per-block engine instantiation (see launch_decompress)
-    int comp_kernel = 3;    // SNP_COMP_KERNEL (1 = baseline, 2 = smem tables, 3 = L2 tables, 4 = 3 + register window,
-                            // 5 = two blocks per warp (half-warps): measured 10-15 % slower than 3, DESIGN.md 4.6;
-                            // 4 measured equal to 3: the kernel is bound by random table sectors)
+    int comp_kernel = 3;    // SNP_COMP_KERNEL: 3 = L2 tables with fingerprinted 32-bit entries (default), 6 = L2 tables with
+                            // the reference's plain 16-bit entries (the challenger), 1 = baseline (tables in shared memory)
     DevBuf d_in, d_out, d_meta, d_tmp;
     DevBuf d_tables;           // k_compress_v3: one 64 KiB hash table slice per resident warp
     cudaEvent_t tables_done = nullptr;  // orders compress launches that arrive on different streams (shared d_tables)
@@ -143,9 +138,6 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kCompWarps = 7;  // 7 x 32 KiB tables + 2 KiB LUT = 226 KiB <= 227 KiB
 constexpr size_t kCompSmem = (size_t)kCompWarps * 32768 + 2048;
-// v2: 6 warps x 32 KiB tables + 2 KiB CRC LUT + probe schedule; the remaining ~30 KiB stay L1
-constexpr int kComp2Warps = 6;
-constexpr size_t kComp2Smem = (size_t)kComp2Warps * 32768 + 2048 + 4 * SNP_SCHED_LEN;
 
 int ctx_set_attrs(snp_ctx *c) {
     if (c->attrs_set) return SNP_OK;
@@ -153,17 +145,11 @@ int ctx_set_attrs(snp_ctx *c) {
                             (int)kCompSmem));
     CU(cudaFuncSetAttribute(snp::k_compress_v1<SNP_HASH_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)kCompSmem));
-    CU(cudaFuncSetAttribute(snp::k_compress_v2<SNP_HASH_CRC32C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)kComp2Smem));
-    CU(cudaFuncSetAttribute(snp::k_compress_v2<SNP_HASH_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)kComp2Smem));
 #define SNP7_ATTR(W, NW, CTAS)                                                                              \
     CU(cudaFuncSetAttribute(snp::k_decompress_v7<W, NW, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                             (int)(NW * sizeof(snp::Warp7<W>))))
     SNP7_ATTR(2048, 8, 5);
-    SNP7_ATTR(2048, 8, 6);
     SNP7_ATTR(4096, 8, 4);
-    SNP7_ATTR(8192, 4, 5);
 #undef SNP7_ATTR
 #define SNP8_ATTR(IR, ORB, D, NT, CTAS, ...)                                                                              \
     CU(cudaFuncSetAttribute(snp::k_decompress_v8<IR, ORB, D, NT, CTAS, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -171,11 +157,7 @@ int ctx_set_attrs(snp_ctx *c) {
     SNP8_ATTR(128, 128, 3, 96, 6);
     SNP8_ATTR(128, 128, 3, 128, 4);
     SNP8_ATTR(128, 128, 4, 128, 4);
-    SNP8_ATTR(128, 128, 2, 96, 6);
-    SNP8_ATTR(256, 256, 3, 64, 5);
     SNP8_ATTR(128, 128, 3, 96, 6, 1);
-    SNP8_ATTR(128, 128, 4, 64, 4, 1);
-    SNP8_ATTR(128, 128, 4, 64, 2, 1);
 #undef SNP8_ATTR
 
     c->attrs_set = true;
@@ -185,7 +167,7 @@ int ctx_set_attrs(snp_ctx *c) {
 // Hands out a zeroed work counter for one persistent launch on stream s (the memset is
 // ordered before the launch).  Counters rotate through a pool so that launches in flight
 // on different streams never share one.
-constexpr unsigned kCounterPool = 64;
+constexpr unsigned kCounterPool = 4096;  // far more than the launches that can be in flight at once
 int ctx_work_counter(snp_ctx *c, cudaStream_t s, unsigned long long **out) {
     if (!c->d_counters) CU(cudaMalloc((void **)&c->d_counters, kCounterPool * 32));
     unsigned long long *p = c->d_counters + 4 * (c->counter_seq++ % kCounterPool);
@@ -210,7 +192,7 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
     const int kernel = c->decomp_kernel;
     const int warps = 8;
     unsigned grid = (unsigned)((n + warps - 1) / warps);
-    if (kernel == 7) {
+    if (kernel != 8 && kernel != 1) {  // 7, the default
         int rc = ctx_set_attrs(c);
         if (rc) return rc;
         unsigned long long *ctr;
@@ -221,9 +203,7 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
         snp::k_decompress_v7<W, NW, CTAS><<<g7, NW * SNP_WARP, NW * sizeof(snp::Warp7<W>), s>>>(                  \
             in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, ctr);                       \
     } while (0)
-        if (c->v7_window == 8192) SNP7_LAUNCH(8192, 4, 5);        // 20 warps per SM, 8 KiB windows
-        else if (c->v7_window == 2048 && c->v7_ctas == 6) SNP7_LAUNCH(2048, 8, 6);  // 48 warps per SM (40 registers)
-        else if (c->v7_window == 2048) SNP7_LAUNCH(2048, 8, 5);   // 40 warps per SM
+        if (c->v7_window == 2048) SNP7_LAUNCH(2048, 8, 5);        // 40 warps per SM, 2 KiB windows (measured 3-4 % slower)
         else SNP7_LAUNCH(4096, 8, 4);                             // 32 warps per SM, 4 KiB windows (default)
 #undef SNP7_LAUNCH
     } else if (kernel == 8) {
@@ -239,25 +219,12 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
     } while (0)
         if (c->v8_cfg == 1) SNP8_LAUNCH(128, 128, 3, 128, 4);       // 512 lanes per SM
         else if (c->v8_cfg == 2) SNP8_LAUNCH(128, 128, 4, 128, 4);  // deeper pipeline
-        else if (c->v8_cfg == 3) SNP8_LAUNCH(128, 128, 2, 96, 6);   // shallower pipeline
-        else if (c->v8_cfg == 4) SNP8_LAUNCH(256, 256, 3, 64, 5);   // 320 lanes per SM, 256-byte rings
-        else if (c->v8_cfg == 5) SNP8_LAUNCH(128, 128, 3, 96, 6, 1);  // 576 lanes, read-once lines evict first
-        else if (c->v8_cfg == 6) SNP8_LAUNCH(128, 128, 4, 64, 4, 1);  // 256 lanes per SM, depth 4, evict first
-        else if (c->v8_cfg == 7) SNP8_LAUNCH(128, 128, 4, 64, 2, 1);  // 128 lanes per SM, depth 4, evict first
+        else if (c->v8_cfg == 5) SNP8_LAUNCH(128, 128, 3, 96, 6, 1);  // 576 lanes, read-once lines evict first in L2
         else SNP8_LAUNCH(128, 128, 3, 96, 6);                       // 576 lanes per SM, 128-byte rings, depth 3
 #undef SNP8_LAUNCH
     } else if (kernel == 1)
         snp::k_decompress_v1<<<grid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
                                                                out_cap, out_len, status, n);
-    else {
-        unsigned long long *ctr;
-        int rc = ctx_work_counter(c, s, &ctr);
-        if (rc) return rc;
-        unsigned pgrid = (unsigned)(c->sm_count * SNP_V3_CTAS);
-        if (pgrid > grid) pgrid = grid;
-        snp::k_decompress_v5<<<pgrid, warps * SNP_WARP, 0, s>>>(in_base, in_off, in_len, out_base, out_off,
-                                                                out_cap, out_len, status, n, ctr);
-    }
     c->launches++;
     CU(cudaGetLastError());
     return SNP_OK;
@@ -276,7 +243,7 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
     // consecutive chunks on different streams: a chunk's CTAs could start in the tail of the previous launch and clear a
     // slice that one of its warps is still using.  Launches on different streams are therefore chained with an event
     // (each launch fills the GPU by itself, so nothing is lost; the copies of the chunks still overlap).
-    const bool shared_tables = c->comp_kernel >= 3 && !own_tables;
+    const bool shared_tables = c->comp_kernel != 1 && !own_tables;
     if (shared_tables) {
         if (!c->tables_done) CU(cudaEventCreateWithFlags(&c->tables_done, cudaEventDisableTiming));
         if (c->tables_used && c->tables_last_stream != s) CU(cudaStreamWaitEvent(s, c->tables_done, 0));
@@ -290,25 +257,8 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
         else
             snp::k_compress_v1<SNP_HASH_MUL><<<grid, kCompWarps * SNP_WARP, kCompSmem, s>>>(
                 in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode);
-    } else if (c->comp_kernel == 5) {
-        // two blocks per warp: one per half-warp (snp_compress_v5.cuh)
-        unsigned long long *ctr;
-        if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
-        constexpr int W = 16;
-        const int gpc = 256 / W;  // lane groups (= blocks in flight) per CTA
-        const int cps = c->comp_ctas_per_sm;
-        const size_t ctas5 = (n + gpc - 1) / gpc;
-        const unsigned grid5 = (unsigned)std::min(ctas5, (size_t)c->sm_count * cps);
-        if ((rc = tables.reserve((size_t)grid5 * gpc * 65536))) return rc;
-        const int fm = frag_mode | (c->comp_first_width << 8);
-        if (hash_mode == SNP_HASH_CRC32C)
-            snp::k_compress_v5<SNP_HASH_CRC32C, W><<<grid5, 256, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap,
-                                                                        out_len, status, n, fm, ctr, (uint32_t *)tables.p);
-        else
-            snp::k_compress_v5<SNP_HASH_MUL, W><<<grid5, 256, 0, s>>>(in_base, in_off, in_len, out_base, out_off, out_cap,
-                                                                     out_len, status, n, fm, ctr, (uint32_t *)tables.p);
-    } else if (c->comp_kernel >= 3) {
-        // hash tables in global memory (L2): occupancy no longer capped by shared memory
+    } else {
+        // hash tables in global memory (L2): occupancy not capped by shared memory
         unsigned long long *ctr;
         if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
         const int wpc = 8;
@@ -322,28 +272,14 @@ int launch_compress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const ui
                                                               out_len, status, n,                                  \
                                                               frag_mode | (c->comp_first_width << 8), ctr,         \
                                                               (uint32_t *)tables.p)
-        if (c->comp_kernel == 3) {
-            if (hash_mode == SNP_HASH_CRC32C) SNP_LAUNCH_C3(SNP_HASH_CRC32C, 3);
-            else SNP_LAUNCH_C3(SNP_HASH_MUL, 3);
-        } else if (c->comp_kernel == 6) {  // plain 16-bit table entries
+        if (c->comp_kernel == 6) {  // plain 16-bit table entries
             if (hash_mode == SNP_HASH_CRC32C) SNP_LAUNCH_C3(SNP_HASH_CRC32C, 6);
             else SNP_LAUNCH_C3(SNP_HASH_MUL, 6);
         } else {
-            if (hash_mode == SNP_HASH_CRC32C) SNP_LAUNCH_C3(SNP_HASH_CRC32C, 4);
-            else SNP_LAUNCH_C3(SNP_HASH_MUL, 4);
+            if (hash_mode == SNP_HASH_CRC32C) SNP_LAUNCH_C3(SNP_HASH_CRC32C, 3);
+            else SNP_LAUNCH_C3(SNP_HASH_MUL, 3);
         }
 #undef SNP_LAUNCH_C3
-    } else {
-        unsigned long long *ctr;
-        if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
-        size_t ctas2 = (n + kComp2Warps - 1) / kComp2Warps;
-        unsigned grid2 = (unsigned)(ctas2 < (size_t)c->sm_count ? ctas2 : (size_t)c->sm_count);
-        if (hash_mode == SNP_HASH_CRC32C)
-            snp::k_compress_v2<SNP_HASH_CRC32C><<<grid2, kComp2Warps * SNP_WARP, kComp2Smem, s>>>(
-                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr);
-        else
-            snp::k_compress_v2<SNP_HASH_MUL><<<grid2, kComp2Warps * SNP_WARP, kComp2Smem, s>>>(
-                in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, frag_mode, ctr);
     }
     c->launches++;
     CU(cudaGetLastError());
@@ -584,7 +520,9 @@ int chunk_phase1(snp_ctx *c, Chunk &ck, bool compress, const uint8_t *in_base, c
     // caller's regions, so its copy can be enqueued right behind the kernel instead of after a host round trip for
     // the produced lengths (bytes of a region beyond out_len are unspecified, as in the device-mode call).
     ck.early_d2h = false;
-    if (!compress && c->host_early_d2h) {
+    // A chunk of ONE item (the single-call API) waits for its status instead: a rejected block must leave the caller's
+    // buffer untouched, as the reference does (it decodes into a private buffer), and only out_len bytes are copied.
+    if (!compress && c->host_early_d2h && n > 1) {
         bool dense = true;
         for (size_t i = ck.a; i + 1 < ck.b && dense; i++) dense = out_off[i + 1] == out_off[i] + out_cap[i];
         if (dense && ck.so.hi > ck.so.lo) {
@@ -727,24 +665,34 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
     return rc;
 }
 
-thread_local std::unique_ptr<snp_ctx, void (*)(snp_ctx *)> g_default_ctx(nullptr, snp_destroy);
+// The single-call API (snp_compress, snp_decompress, snp_frame_*: what sits behind Snappy.Compress / Decompress, called
+// from arbitrary thread-pool threads) shares ONE context per device, created on first use and alive until the process
+// exits.  Calls serialise on the context's mutex -- a call fills the GPU by itself -- so device scratch does not grow with
+// the number of calling threads.  Footprint: the pipeline slots' buffers follow the largest call so far (about 2.2 x the
+// chunk size per slot in use, 64 MiB chunks by default); hash tables follow the largest compress launch (64 KiB per
+// concurrently compressed 64 KiB block, 512 KiB for a one-block call).
+constexpr int kMaxDevices = 64;
+std::mutex g_default_mu;
+snp_ctx *g_default_ctx[kMaxDevices];  // never destroyed: the driver reclaims the memory at process exit
 
 int default_ctx(snp_ctx **out) {
-    if (!g_default_ctx) {
-        int dev = 0;
-        int cnt = 0;
-        cudaError_t e = cudaGetDeviceCount(&cnt);
-        if (e != cudaSuccess || cnt == 0) {
-            cuda_fail(e == cudaSuccess ? cudaErrorNoDevice : e, "cudaGetDeviceCount", __LINE__);
-            return SNP_E_NO_DEVICE;
-        }
-        CU(cudaGetDevice(&dev));
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cuda_fail(e == cudaSuccess ? cudaErrorNoDevice : e, "cudaGetDeviceCount", __LINE__);
+        return SNP_E_NO_DEVICE;
+    }
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return SNP_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default_ctx[dev]) {
         snp_ctx *c = nullptr;
         int rc = snp_create(dev, &c);
         if (rc) return rc;
-        g_default_ctx.reset(c);
+        g_default_ctx[dev] = c;
     }
-    *out = g_default_ctx.get();
+    *out = g_default_ctx[dev];
     return SNP_OK;
 }
 
@@ -872,6 +820,21 @@ int compress_fragments_locked(snp_ctx *c, const uint8_t *const *seg_ptr, const s
 
 // ------------------------------------------------------------------ C ABI ----
 
+// No C++ exception may cross the C ABI (P/Invoke, ctypes): every entry point that can allocate is a function-try-block.
+#define SNP_ABI_CATCH                                              \
+    catch (const std::bad_alloc &) {                               \
+        g_last_error = "out of host memory";                       \
+        return SNP_E_NOMEM;                                        \
+    }                                                              \
+    catch (const std::exception &e) {                              \
+        g_last_error = std::string("internal error: ") + e.what(); \
+        return SNP_E_INTERNAL;                                     \
+    }                                                              \
+    catch (...) {                                                  \
+        g_last_error = "internal error";                           \
+        return SNP_E_INTERNAL;                                     \
+    }
+
 extern "C" {
 
 int snp_abi_version(void) { return SNP_ABI_VERSION; }
@@ -889,6 +852,10 @@ const char *snp_status_string(int st) {
         case SNP_E_CUDA: return "CUDA error";
         case SNP_E_INVALID_ARG: return "invalid argument";
         case SNP_E_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        case SNP_E_NOMEM:
+            return "out of host memory";
+        case SNP_E_INTERNAL:
+            return "internal error";
         case SNP_E_OVERLAP: return "Input and output spans must not overlap.";
         default: return "unknown status";
     }
@@ -910,7 +877,7 @@ int snp_uncompressed_length(const uint8_t *in, size_t n, uint32_t *len) {
     return SNP_OK;
 }
 
-int snp_create(int device, snp_ctx **out) {
+int snp_create(int device, snp_ctx **out) try {
     if (!out) return SNP_E_INVALID_ARG;
     *out = nullptr;
     int cnt = 0;
@@ -939,7 +906,6 @@ int snp_create(int device, snp_ctx **out) {
     CU(cudaStreamSynchronize(c->stream));
     c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 7);
     c->v7_window = env_int("SNP_V7_WINDOW", 4096);
-    c->v7_ctas = env_int("SNP_V7_CTAS", 0);
     c->v8_cfg = env_int("SNP_V8_CFG", 0);
     if (const int l2g = env_int("SNP_L2_FETCH", 0)) {  // experiment: DRAM -> L2 fetch granularity (32 / 64 / 128 bytes)
         CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2g));
@@ -955,7 +921,7 @@ int snp_create(int device, snp_ctx **out) {
     c->host_trace = env_int("SNP_HOST_TRACE", 0);
     *out = c.release();
     return SNP_OK;
-}
+} SNP_ABI_CATCH
 
 void snp_destroy(snp_ctx *c) {
     if (!c) return;
@@ -978,7 +944,7 @@ uint64_t snp_ctx_launch_count(const snp_ctx *c) { return c ? c->launches.load() 
 
 int snp_compress_batch(snp_ctx *c, const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
                        uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
-                       int32_t *status, size_t n, uint32_t hash_mode, int mem_kind, void *stream) {
+                       int32_t *status, size_t n, uint32_t hash_mode, int mem_kind, void *stream) try {
     if (hash_mode > SNP_HASH_MUL || (mem_kind != SNP_MEM_HOST && mem_kind != SNP_MEM_DEVICE))
         return SNP_E_INVALID_ARG;
     if (n && (!in_off || !in_len || !out_off || !out_cap || !out_len || !status || !out_base))
@@ -992,11 +958,11 @@ int snp_compress_batch(snp_ctx *c, const uint8_t *in_base, const uint64_t *in_of
                                out_off, out_cap, out_len, status, n, hash_mode, 0);
     return run_host_batch(c, true, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n,
                           hash_mode);
-}
+} SNP_ABI_CATCH
 
 int snp_decompress_batch(snp_ctx *c, const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
                          uint8_t *out_base, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len,
-                         int32_t *status, size_t n, int mem_kind, void *stream) {
+                         int32_t *status, size_t n, int mem_kind, void *stream) try {
     if (mem_kind != SNP_MEM_HOST && mem_kind != SNP_MEM_DEVICE) return SNP_E_INVALID_ARG;
     if (n && (!in_base || !in_off || !in_len || !out_off || !out_cap || !out_len || !status))
         return SNP_E_INVALID_ARG;
@@ -1008,11 +974,11 @@ int snp_decompress_batch(snp_ctx *c, const uint8_t *in_base, const uint64_t *in_
         return launch_decompress(c, (cudaStream_t)stream, in_base, in_off, in_len,
                                  out_base, out_off, out_cap, out_len, status, n);
     return run_host_batch(c, false, in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, 0);
-}
+} SNP_ABI_CATCH
 
 int snp_uncompressed_length_batch(snp_ctx *c, const uint8_t *in_base, const uint64_t *in_off,
                                   const uint32_t *in_len, uint32_t *ulen, int32_t *status, size_t n,
-                                  int mem_kind, void *stream) {
+                                  int mem_kind, void *stream) try {
     if (mem_kind != SNP_MEM_HOST && mem_kind != SNP_MEM_DEVICE) return SNP_E_INVALID_ARG;
     if (n && (!in_base || !in_off || !in_len || !ulen || !status)) return SNP_E_INVALID_ARG;
     if (n == 0) return SNP_OK;
@@ -1031,9 +997,9 @@ int snp_uncompressed_length_batch(snp_ctx *c, const uint8_t *in_base, const uint
     c->launches++;
     CU(cudaGetLastError());
     return SNP_OK;
-}
+} SNP_ABI_CATCH
 
-int snp_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written, uint32_t hash_mode) {
+int snp_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written, uint32_t hash_mode) try {
     if (!written || (!in && n) || (!out && cap) || hash_mode > SNP_HASH_MUL || n > 0xffffffffull)
         return SNP_E_INVALID_ARG;
     *written = 0;
@@ -1068,10 +1034,10 @@ int snp_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *
     const uint8_t *one_ptr[1] = {in};
     const size_t one_len[1] = {n};
     return compress_fragments_locked(c, one_ptr, one_len, 1, n, len, out, cap, written, hash_mode);
-}
+} SNP_ABI_CATCH
 
 int snp_compress_sequence(const uint8_t *const *seg_ptr, const size_t *seg_len, size_t n_seg, uint8_t *out, size_t cap,
-                          size_t *written, uint32_t hash_mode) {
+                          size_t *written, uint32_t hash_mode) try {
     if (!written || (n_seg && (!seg_ptr || !seg_len)) || (!out && cap) || hash_mode > SNP_HASH_MUL)
         return SNP_E_INVALID_ARG;
     *written = 0;
@@ -1111,10 +1077,10 @@ int snp_compress_sequence(const uint8_t *const *seg_ptr, const size_t *seg_len, 
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
     return compress_fragments_locked(c, seg_ptr, seg_len, n_seg, n, len, out, cap, written, hash_mode);
-}
+} SNP_ABI_CATCH
 
 int snp_decompress_sequence(const uint8_t *const *seg_ptr, const size_t *seg_len, size_t n_seg, uint8_t *out,
-                            size_t cap, size_t *written) {
+                            size_t cap, size_t *written) try {
     // Snappy.Decompress(ReadOnlySequence<byte>, ..) feeds the segments to one decoder in order (Snappy.cs:194-212,
     // 246-261): the result is that of decoding their concatenation.  The batch engine needs whole blocks, so the
     // segments are joined on the host first (the resumable split-input state machine stays out of scope).
@@ -1133,9 +1099,9 @@ int snp_decompress_sequence(const uint8_t *const *seg_ptr, const size_t *seg_len
         o += seg_len[i];
     }
     return snp_decompress(joined.data(), n, out, cap, written);
-}
+} SNP_ABI_CATCH
 
-int snp_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written) {
+int snp_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written) try {
     if (!written || (!in && n) || (!out && cap) || n > 0xffffffffull) return SNP_E_INVALID_ARG;
     *written = 0;
     uint32_t U;
@@ -1161,21 +1127,29 @@ int snp_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t
     // decodes the whole block into its own buffer first, so data errors win over
     // "too small", and Read() then hands back the first `cap` bytes
     // (Snappy.cs:172-186, SnappyDecompressor.cs:613-629).
-    std::vector<uint8_t> full(U ? U : 1);
-    rc = run_host_batch(c, false, in, &zero, &in_len, full.data(), &zero, &out_cap, &out_len, &bst, 1, 0);
+    // The declared length comes from an untrusted header: a block of n bytes cannot produce more than 64 bytes per 3-byte
+    // copy tag, and the pipeline only ever copies the bytes a block produced, so the private buffer is bounded by the
+    // input size (a 13-byte block that announces 2 GiB costs 350 bytes, not 2 GiB); no zero fill.
+    const size_t need = std::max<size_t>(std::min<uint64_t>(U, 22ull * n + 64), 1);
+    std::unique_ptr<uint8_t, void (*)(void *)> full((uint8_t *)malloc(need), free);
+    if (!full) {
+        g_last_error = "out of host memory";
+        return SNP_E_NOMEM;
+    }
+    rc = run_host_batch(c, false, in, &zero, &in_len, full.get(), &zero, &out_cap, &out_len, &bst, 1, 0);
     if (rc) return rc;
     if (bst != SNP_OK) return bst;
-    memcpy(out, full.data(), cap);
+    memcpy(out, full.get(), cap);
     *written = cap;
     return SNP_OUTPUT_TOO_SMALL;
-}
+} SNP_ABI_CATCH
 
 // ------------------------------------------------------------- framing format --
 
 size_t snp_frame_max_compressed_length(size_t n) { return 10 + n + 8 * ((n + SNP_BLOCK_SIZE - 1) / SNP_BLOCK_SIZE); }
 
 int snp_pack_batch(snp_ctx *c, const uint8_t *src_base, const uint64_t *src_off, const uint32_t *len, size_t n,
-                   uint8_t *dst_base, uint64_t *dst_off, uint64_t *total, void *stream) {
+                   uint8_t *dst_base, uint64_t *dst_off, uint64_t *total, void *stream) try {
     if (!c || (n && (!src_base || !src_off || !len || !dst_off)) || !total) return SNP_E_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
@@ -1200,10 +1174,10 @@ int snp_pack_batch(snp_ctx *c, const uint8_t *src_base, const uint64_t *src_off,
     c->launches += 3;
     CU(cudaGetLastError());
     return SNP_OK;
-}
+} SNP_ABI_CATCH
 
 int snp_crc32c_batch(snp_ctx *c, const uint8_t *base, const uint64_t *off, const uint32_t *len, uint32_t *crc,
-                     size_t n, int masked, int mem_kind, void *stream) {
+                     size_t n, int masked, int mem_kind, void *stream) try {
     if (mem_kind != SNP_MEM_HOST && mem_kind != SNP_MEM_DEVICE) return SNP_E_INVALID_ARG;
     if (n && (!base || !off || !len || !crc)) return SNP_E_INVALID_ARG;
     if (n == 0) return SNP_OK;
@@ -1238,9 +1212,9 @@ int snp_crc32c_batch(snp_ctx *c, const uint8_t *base, const uint64_t *off, const
     CU(cudaMemcpyAsync(crc, dm + mo + ml, n * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return SNP_OK;
-}
+} SNP_ABI_CATCH
 
-int snp_frame_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written, uint32_t hash_mode) {
+int snp_frame_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written, uint32_t hash_mode) try {
     static const uint8_t kStreamId[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};
     if (!written || (!in && n) || (!out && cap) || hash_mode > SNP_HASH_MUL) return SNP_E_INVALID_ARG;
     *written = 0;
@@ -1310,7 +1284,7 @@ int snp_frame_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, si
     CU(cudaStreamSynchronize(s));
     *written = total;
     return SNP_OK;
-}
+} SNP_ABI_CATCH
 
 namespace {
 struct FrameChunk {
@@ -1356,15 +1330,15 @@ int frame_scan(const uint8_t *in, size_t n, std::vector<FrameChunk> &chunks, uin
 }
 }  // namespace
 
-int snp_frame_uncompressed_length(const uint8_t *in, size_t n, uint64_t *len) {
+int snp_frame_uncompressed_length(const uint8_t *in, size_t n, uint64_t *len) try {
     if (!len || (!in && n)) return SNP_E_INVALID_ARG;
     std::vector<FrameChunk> chunks;
     int st = frame_scan(in, n, chunks, len);
     if (st != SNP_OK) *len = 0;
     return st;
-}
+} SNP_ABI_CATCH
 
-int snp_frame_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written) {
+int snp_frame_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *written) try {
     if (!written || (!in && n) || (!out && cap)) return SNP_E_INVALID_ARG;
     *written = 0;
     std::vector<FrameChunk> chunks;
@@ -1448,6 +1422,6 @@ int snp_frame_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, 
     CU(cudaStreamSynchronize(s));
     *written = (size_t)total;
     return SNP_OK;
-}
+} SNP_ABI_CATCH
 
 }  // extern "C"

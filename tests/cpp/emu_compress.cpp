@@ -1,10 +1,10 @@
-// emu_compress.cpp -- runs the compress fragment functions (k_compress_v3's default path, the register-window variant
-// v4 and the v1 baseline) on the host SIMT emulator.  TEST INFRASTRUCTURE ONLY (see simt_emu.h).
-// Usage: emu_compress <batch-in> <result-out> <variant: 1|3|4|6> <hash: 0|1> <first-width>
+// emu_compress.cpp -- runs the compress fragment functions (k_compress_v3's default path, its 16-bit-entry variant and
+// the v1 baseline) on the host SIMT emulator.  TEST INFRASTRUCTURE ONLY (see simt_emu.h).
+// Usage: emu_compress <batch-in> <result-out> <variant: 1|3|6> <hash: 0|1> <first-width>
 //   batch-in : u32 n, then per item { u32 len, bytes }      result: per item { u32 out_len, bytes }
 #include "simt_emu.h"
 #define SNP_EMU 1
-#include "../../snappier_b200/csrc/snp_compress_v2.cuh"
+#include "../../snappier_b200/csrc/snp_compress_v3.cuh"
 
 #include <vector>
 
@@ -35,7 +35,6 @@ static void run(const uint8_t *in, uint32_t n, snp::OutCursor &o, int variant, u
         oc.pos = need;
         if (n > 0) {
             if (variant == 1) snp::compress_fragment_v1<HASH>(in, n, oc, (uint16_t *)table, lut);
-            else if (variant == 4) snp::compress_fragment_v4<HASH>(in, n, oc, (uint32_t *)table, lut, sched);
             else if (variant == 6) snp::compress_fragment_v3<HASH, false>(in, n, oc, (uint32_t *)table, lut, sched, w0);
             else snp::compress_fragment_v3<HASH, true>(in, n, oc, (uint32_t *)table, lut, sched, w0);
         }

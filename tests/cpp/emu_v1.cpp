@@ -1,9 +1,11 @@
-// emu_v5.cpp -- runs the default decompress engine's block functions (v5 = sparse prefix engine + v3 dense engine,
-// plus the v1 baseline) on the host SIMT emulator.  TEST INFRASTRUCTURE ONLY (see simt_emu.h).
-// Usage: emu_v5 <batch-in> <result-out> <engine: 1|3|5>   (same file formats as emu_v6)
+// emu_v1.cpp -- runs the baseline decompress block function (decompress_block_v1: the > 2 GiB / big-block path of the
+// fast engines and the A/B reference) on the host SIMT emulator.  TEST INFRASTRUCTURE ONLY (see simt_emu.h).
+// Usage: emu_v1 <batch-in> <result-out> 1
+//   batch-in: u32 n, then per item { u32 in_len, u32 cap, u32 in_misalign, u32 out_misalign, bytes }
+//   result  : per item { i32 status, u32 written, u32 guard_ok, cap bytes of output }
 #include "simt_emu.h"
 #define SNP_EMU 1
-#include "../../snappier_b200/csrc/snp_decompress_v5.cuh"
+#include "../../snappier_b200/csrc/snp_decompress_v1.cuh"
 
 #include <vector>
 
@@ -24,15 +26,11 @@ static std::vector<uint8_t> slurp(const char *p) {
 
 int main(int argc, char **argv) {
     if (argc < 4) return 2;
-    const int engine = atoi(argv[3]);
     const std::vector<uint8_t> raw = slurp(argv[1]);
     const uint8_t *p = raw.data();
     uint32_t n;
     memcpy(&n, p, 4);
     p += 4;
-    uint32_t lut[256];
-    for (int c = 0; c < 256; c++) lut[c] = snp::tag_lut3_entry(c);
-    snp::WarpQueue3 *q = (snp::WarpQueue3 *)aligned_alloc(16, sizeof(snp::WarpQueue3));
     FILE *f = fopen(argv[2], "wb");
     for (uint32_t i = 0; i < n; i++) {
         uint32_t h[4];
@@ -48,9 +46,7 @@ int main(int argc, char **argv) {
         int st = -77;
         simt::run_warp([&] {
             uint32_t ww = 0;
-            int s = engine == 1   ? snp::decompress_block_v1(in, in_len, out, cap, &ww)
-                    : engine == 3 ? snp::decompress_block_v3(in, in_len, out, cap, &ww, lut, q)
-                                  : snp::decompress_block_v5(in, in_len, out, cap, &ww, lut, q);
+            int s = snp::decompress_block_v1(in, in_len, out, cap, &ww);
             if (simt::lane() == 0) {
                 w = ww;
                 st = s;
@@ -65,6 +61,5 @@ int main(int argc, char **argv) {
         fwrite(out, 1, cap, f);
     }
     fclose(f);
-    free(q);
     return 0;
 }

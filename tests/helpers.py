@@ -181,3 +181,57 @@ def handmade_tag_forms() -> list[bytes]:
             total += ln
     items.append(varint(total) + bytes(body))
     return items
+
+
+# ---- host-emulator harness protocol shared by tests/test_emu_v{1,7,8}.py (tests/cpp/emu_v*.cpp) -----------------------
+
+def emu_run(exe, items, caps, tmp_path, engine, seed):
+    """Writes the batch file, runs the emulator binary, parses (status, written, guard_ok, output) per item."""
+    import struct
+    import subprocess
+    rng = np.random.default_rng(seed)
+    blob = bytearray(struct.pack("<I", len(items)))
+    for b, cap in zip(items, caps):
+        blob += struct.pack("<IIII", len(b), cap, int(rng.integers(0, 16)), int(rng.integers(0, 16))) + b
+    fin, fout = os.path.join(tmp_path, "batch.bin"), os.path.join(tmp_path, "result.bin")
+    with open(fin, "wb") as f:
+        f.write(blob)
+    subprocess.check_call([exe, fin, fout, str(engine)], timeout=1500)
+    raw = open(fout, "rb").read()
+    res, p = [], 0
+    for cap in caps:
+        st, n, guard = struct.unpack_from("<iII", raw, p)
+        p += 12
+        res.append((st, n, guard, raw[p:p + cap]))
+        p += cap
+    return res
+
+
+def emu_check(oracle, exe, items, tmp_path, engine, seed=0):
+    """Status, length, bytes and guard bytes of every item against the oracle."""
+    caps = []
+    for b in items:
+        st, n = oracle.uncompressed_length(b)
+        caps.append(min(n, 1 << 22) if st == 0 else 0)
+    res = emu_run(exe, items, caps, str(tmp_path), engine, seed)
+    for i, (b, cap) in enumerate(zip(items, caps)):
+        st, dec = oracle.decompress(b, cap=cap)
+        gst, gn, guard, out = res[i]
+        assert gst == st, (engine, i, b[:16], gst, st)
+        assert guard == 1, (engine, i, "wrote outside its output region")
+        assert gn == len(dec) and out[:gn] == dec, (engine, i)
+
+
+def bad_blocks(oracle, fixtures):
+    """The reference's corrupt fixtures and the malformed-stream cases of SnappyTests.cs:212-331."""
+    bad = [fixtures[f"bad/baddata{i}.snappy"] for i in (1, 2, 3)]
+    c = bytearray(oracle.compress(b"making sure we don't crash with corrupted input")[1])
+    c[1] -= 1
+    c[3] += 1
+    bad.append(bytes(c))
+    c = bytearray(oracle.compress(b"A" * 1000)[1])
+    c[0], c[1] = 255, 127
+    bad.append(bytes(c))
+    return bad + [b"", b"\x80", b"\xff" * 6, b"\xff\xff\xff\xff\x1f", b"\x05\x10abc", b"\x04\x0cabcd\x01\x00",
+                  b"\x08\x0cabcd\x05\x09", b"\x03\x0cabcd", b"\x04\xf0", b"\x0a\x00a\xfe\x01\x00\x00",
+                  b"\x40\x00a\xfe\x01\x00", b"\x00garbage", b"\x02\x04ab\x00c"]

@@ -11,7 +11,6 @@ import numpy as np
 import pytest
 
 from tests import helpers as H
-from tests.test_emu_v5 import _bad_blocks, _check
 from tests.helpers import BUILD, ROOT, handmade_tag_forms
 
 
@@ -31,12 +30,12 @@ def emu7():
 def test_emu_v7_blocks(oracle, fixtures, kats, emu7, tmp_path, window):
     items = [oracle.compress(s)[1] for s in H.edge_strings(kats)]
     items += [oracle.compress(b)[1] for b in (b"", b"a", b"abc" * 100, b"\x00" * 65536, b"ab" * 700 + b"c" * 3000)]
-    items += _bad_blocks(oracle, fixtures)
+    items += H.bad_blocks(oracle, fixtures)
     for name in ("alice29.txt", "html", "kppkn.gtb", "fireworks.jpeg", "geo.protodata", "urls.10K"):
         blocks = H.blocks_of(fixtures[f"corpus/{name}"])
         items += [oracle.compress(blocks[0])[1], oracle.compress(blocks[-1])[1]]
     items += [oracle.compress(b)[1] for b in H.synthetic_blocks(5, 6)]
-    _check(oracle, emu7, items, tmp_path, window, seed=window)
+    H.emu_check(oracle, emu7, items, tmp_path, window, seed=window)
 
 
 def test_emu_v7_handmade_and_fuzz(oracle, emu7, tmp_path):
@@ -50,7 +49,7 @@ def test_emu_v7_handmade_and_fuzz(oracle, emu7, tmp_path):
         if i % 5 == 0:
             b = b[: int(rng.integers(0, len(b)))]
         items.append(bytes(b))
-    _check(oracle, emu7, items, tmp_path, 2048, seed=9)
+    H.emu_check(oracle, emu7, items, tmp_path, 2048, seed=9)
 
 
 def test_emu_v7_multi_fragment_and_ragged(oracle, fixtures, emu7, tmp_path):
@@ -65,4 +64,4 @@ def test_emu_v7_multi_fragment_and_ragged(oracle, fixtures, emu7, tmp_path):
     # literal runs of every length 500..530 between compressible stretches
     for n in range(500, 531, 3):
         items.append(oracle.compress(b"x" * 100 + rng.integers(0, 256, size=n, dtype=np.uint8).tobytes() + b"y" * 3000)[1])
-    _check(oracle, emu7, items, tmp_path, 2048, seed=11)
+    H.emu_check(oracle, emu7, items, tmp_path, 2048, seed=11)

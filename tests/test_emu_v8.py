@@ -12,7 +12,6 @@ import numpy as np
 import pytest
 
 from tests import helpers as H
-from tests.test_emu_v5 import _bad_blocks, _check
 from tests.helpers import BUILD, ROOT, handmade_tag_forms
 
 
@@ -32,12 +31,12 @@ def emu8():
 def test_emu_v8_blocks(oracle, fixtures, kats, emu8, tmp_path, oring):
     items = [oracle.compress(s)[1] for s in H.edge_strings(kats)]
     items += [oracle.compress(b)[1] for b in (b"", b"a", b"abc" * 100, b"\x00" * 65536, b"ab" * 700 + b"c" * 3000)]
-    items += _bad_blocks(oracle, fixtures)
+    items += H.bad_blocks(oracle, fixtures)
     for name in ("alice29.txt", "html", "kppkn.gtb", "fireworks.jpeg", "geo.protodata", "urls.10K"):
         blocks = H.blocks_of(fixtures[f"corpus/{name}"])
         items += [oracle.compress(blocks[0])[1], oracle.compress(blocks[-1])[1]]
     items += [oracle.compress(b)[1] for b in H.synthetic_blocks(5, 6)]
-    _check(oracle, emu8, items, tmp_path, oring, seed=oring)
+    H.emu_check(oracle, emu8, items, tmp_path, oring, seed=oring)
 
 
 def test_emu_v8_handmade_and_fuzz(oracle, emu8, tmp_path):
@@ -51,7 +50,7 @@ def test_emu_v8_handmade_and_fuzz(oracle, emu8, tmp_path):
         if i % 5 == 0:
             b = b[: int(rng.integers(0, len(b)))]
         items.append(bytes(b))
-    _check(oracle, emu8, items, tmp_path, 128, seed=9)
+    H.emu_check(oracle, emu8, items, tmp_path, 128, seed=9)
 
 
 def test_emu_v8_big_blocks_ragged_and_long_literals(oracle, fixtures, emu8, tmp_path):
@@ -70,4 +69,4 @@ def test_emu_v8_big_blocks_ragged_and_long_literals(oracle, fixtures, emu8, tmp_
     for period in range(1, 20):   # overlapping copies of every short period, then a far reference back into them
         pat = bytes(rng.integers(0, 256, size=period, dtype=np.uint8))
         items.append(oracle.compress(pat * 300 + rng.integers(0, 256, size=500, dtype=np.uint8).tobytes() + pat * 40)[1])
-    _check(oracle, emu8, items, tmp_path, 128, seed=11)
+    H.emu_check(oracle, emu8, items, tmp_path, 128, seed=11)

@@ -337,8 +337,8 @@ def test_device_mode_large_batch_properties(engine, oracle):
     ch = comp.view(n, pitch)
     for i in (0, 1, 63, 64, 2047, 4095):
         assert ch[i, : cl[i]].cpu().numpy().tobytes() == oracle.compress(blocks[i % len(blocks)])[1]
-    # the 2 KiB-window instantiation of the default kernel and the round-1 kernel on the same device-resident batch
-    for env in ({"SNP_V7_WINDOW": "2048"}, {"SNP_DECOMP_KERNEL": "5"}):
+    # the 2 KiB-window instantiation of the default kernel and the lane-per-block engine on the same device-resident batch
+    for env in ({"SNP_V7_WINDOW": "2048"}, {"SNP_DECOMP_KERNEL": "8"}, {"SNP_DECOMP_KERNEL": "8", "SNP_V8_CFG": "2"}):
         ex = _engine_with(env)
         out.zero_()
         o_len.zero_()
@@ -373,13 +373,13 @@ def test_baseline_kernels_agree_with_fast_kernels(oracle, fixtures):
     e1 = _engine_with({"SNP_DECOMP_KERNEL": "1", "SNP_COMP_KERNEL": "1"})
     e2 = _engine_with({})                            # default: tag-group engine, 4 KiB output window
     e4 = _engine_with({"SNP_V7_WINDOW": "2048"})     # the same engine with a 2 KiB window (40 warps per SM)
-    e5 = _engine_with({"SNP_DECOMP_KERNEL": "5"})    # round-1 default: sparse-tag prefix engine + speculative dense engine
+    e5 = _engine_with({"SNP_DECOMP_KERNEL": "8"})    # the challenger: lane-per-block engine
     _, blocks = _corpus_blocks(fixtures)
     blocks = blocks + H.synthetic_blocks(5150, 48)
     c1, s1 = compress_many(e1, blocks, 0)
     c2, s2 = compress_many(e2, blocks, 0)
     assert c1 == c2 and not s1.any() and not s2.any()
-    for variant in ("2", "4", "5", "6"):  # smem tables; L2 tables + register window; half-warps; 16-bit L2 tables
+    for variant in ("6",):  # the challenger: plain 16-bit table entries in L2
         ev = _engine_with({"SNP_COMP_KERNEL": variant})
         for mode in (0, 1):
             cv, sv = compress_many(ev, blocks, mode)
