@@ -195,6 +195,13 @@ int snp_frame_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, 
 int snp_pack_batch(snp_ctx *ctx, const uint8_t *src_base, const uint64_t *src_off, const uint32_t *len, size_t n_items,
                    uint8_t *dst_base, uint64_t *dst_off, uint64_t *total, void *stream);
 
+/* Batched SnappyCompressor.FindMatchLength (SnappyCompressor.cs:562-688): matched[i] = length of the common prefix of
+ * base[s1[i]..] and base[s2[i]..s2_limit[i]) -- the compress kernels' own device function behind an entry point, so that the
+ * reference's known-answer vectors (Snappier.Tests/Internal/SnappyCompressorTests.cs:10-81) run on the GPU directly.
+ * DEVICE pointers only; enqueued on `stream`. */
+int snp_find_match_length_batch(snp_ctx *ctx, const uint8_t *base, const uint32_t *s1, const uint32_t *s2,
+                                const uint32_t *s2_limit, uint32_t *matched, size_t n_items, void *stream);
+
 /* Batched Crc32CAlgorithm.Compute (+ ApplyMask when masked != 0), Crc32CAlgorithm.cs:41-44,157-158. */
 int snp_crc32c_batch(snp_ctx *ctx, const uint8_t *base, const uint64_t *off, const uint32_t *len,
                      uint32_t *crc, size_t n_items, int masked, int mem_kind, void *stream);

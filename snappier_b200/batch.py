@@ -100,6 +100,17 @@ class Engine:
         N.check_call(rc, "snp_pack_batch")
         return dst_off, total
 
+    def find_match_length_batch_device(self, base, s1, s2, s2_limit, stream: int | None = None):
+        """Batched SnappyCompressor.FindMatchLength on the device (u8 base, i32 positions); returns i32[N] on the device."""
+        import torch
+        n = s1.numel()
+        out = torch.zeros(n, dtype=torch.int32, device=s1.device)
+        rc = N.lib().snp_find_match_length_batch(
+            self._ctx, self._check_dev(base, 1, "base"), self._check_dev(s1, 4, "s1"), self._check_dev(s2, 4, "s2"),
+            self._check_dev(s2_limit, 4, "s2_limit"), out.data_ptr(), n, stream)
+        N.check_call(rc, "snp_find_match_length_batch")
+        return out
+
     # --------------------------------------------------------------- host mode
     def compress_batch_host(self, in_base: np.ndarray, in_off, in_len, out_base: np.ndarray, out_off,
                             out_cap, hash_mode: int = N.HASH_CRC32C):

@@ -115,6 +115,7 @@ struct snp_ctx {
     std::vector<TraceRow> trace;
     int host_early_d2h = 1;  // SNP_HOST_EARLY_D2H: enqueue the payload copy of dense decompress chunks behind the kernel
     uint64_t host_chunk_bytes = 64ull << 20;   // host-mode pipeline: bytes per chunk (SNP_HOST_CHUNK_MB)
+    uint64_t host_comp_chunk_bytes = 256ull << 20;  // the same for compress calls (SNP_HOST_COMP_CHUNK_MB): raw bytes per chunk
     int comp_first_width = 16;  // SNP_COMP_FIRST_WIDTH: probes in the first batch after a match (k_compress_v3; 32 = fixed width)
     unsigned long long *d_counters = nullptr;  // pool of work counters for the persistent kernels
     unsigned counter_seq = 0;
@@ -122,7 +123,7 @@ struct snp_ctx {
     struct Slot {
         cudaStream_t stream = nullptr;
         cudaEvent_t meta_ready = nullptr;
-        DevBuf d_in, d_out, d_meta;
+        DevBuf d_in, d_out, d_meta, d_tmp;
         DevBuf d_tables;   // hash tables of this slot's compress launches (sized by the chunk's grid): the chunks of the
                            // host-mode pipeline compress concurrently, each on its slot's stream
         PinnedBuf h_meta;  // same layout as d_meta: async both ways regardless of the caller's arrays
@@ -335,6 +336,19 @@ __global__ void k_frag_gather(const uint8_t *__restrict__ tmp, size_t pitch, con
         uint8_t *d = out + off[f];
         uint32_t l = len[f];
         for (uint32_t k = threadIdx.x; k < l; k += blockDim.x) d[k] = s[k];
+    }
+}
+
+// Batched SnappyCompressor.FindMatchLength (SnappyCompressor.cs:562-688): one warp per query, the compress kernels'
+// own device function -- so that the reference's known-answer vectors run on the GPU directly.
+__global__ void __launch_bounds__(256) k_find_match_length(const uint8_t *__restrict__ base, const uint32_t *__restrict__ s1,
+                                                           const uint32_t *__restrict__ s2, const uint32_t *__restrict__ limit,
+                                                           uint32_t *__restrict__ out, size_t n) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (size_t i = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+        const uint32_t m = snp::find_match_length_v2(base, s1[i], s2[i], limit[i], lane);
+        if (lane == 0) out[i] = m;
     }
 }
 
@@ -603,7 +617,9 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
         if (!sl.stream) CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         if (!sl.meta_ready) CU(cudaEventCreateWithFlags(&sl.meta_ready, cudaEventDisableTiming));
     }
-    const uint64_t kChunkBytes = c->host_chunk_bytes;  // per-chunk output span target (SNP_HOST_CHUNK_MB)
+    // per-chunk span target: the output span of a decompress chunk (SNP_HOST_CHUNK_MB), the input span of a compress chunk
+    // (SNP_HOST_COMP_CHUNK_MB; its output span -- slots with slack -- is allowed to be proportionally larger)
+    const uint64_t kChunkBytes = compress ? c->host_comp_chunk_bytes : c->host_chunk_bytes;
     constexpr size_t kChunkItems = 16384;
     // Phase 2 of a chunk (wait for its lengths / statuses, copy them to the caller, enqueue the payload copy when it was
     // not enqueued early) runs kLag chunks behind phase 1: waiting for chunk k-1's kernel before enqueueing chunk k+1
@@ -624,7 +640,7 @@ int run_host_batch(snp_ctx *c, bool compress, const uint8_t *in_base, const uint
         while (b < n && b - a < kChunkItems) {
             uint64_t nilo = std::min(ilo, in_off[b]), nihi = std::max(ihi, in_off[b] + in_len[b]);
             uint64_t nolo = std::min(olo, out_off[b]), nohi = std::max(ohi, out_off[b] + out_cap[b]);
-            if (b > a && (nohi - nolo > limit || nihi - nilo > limit)) break;
+            if (b > a && (nihi - nilo > limit || (!compress && nohi - nolo > limit))) break;
             ilo = nilo, ihi = nihi, olo = nolo, ohi = nohi;
             b++;
         }
@@ -917,6 +933,7 @@ int snp_create(int device, snp_ctx **out) try {
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));
     c->host_chunk_bytes = (uint64_t)std::max(1, env_int("SNP_HOST_CHUNK_MB", 64)) << 20;
+    c->host_comp_chunk_bytes = (uint64_t)std::max(1, env_int("SNP_HOST_COMP_CHUNK_MB", 256)) << 20;
     c->host_early_d2h = env_int("SNP_HOST_EARLY_D2H", 1);
     c->host_trace = env_int("SNP_HOST_TRACE", 0);
     *out = c.release();
@@ -1176,6 +1193,19 @@ int snp_pack_batch(snp_ctx *c, const uint8_t *src_base, const uint64_t *src_off,
     return SNP_OK;
 } SNP_ABI_CATCH
 
+int snp_find_match_length_batch(snp_ctx *c, const uint8_t *base, const uint32_t *s1, const uint32_t *s2,
+                                const uint32_t *s2_limit, uint32_t *matched, size_t n, void *stream) try {
+    if (!c || (n && (!base || !s1 || !s2 || !s2_limit || !matched))) return SNP_E_INVALID_ARG;
+    if (n == 0) return SNP_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    const unsigned grid = (unsigned)std::min((n + 7) / 8, (size_t)c->sm_count * 8);
+    k_find_match_length<<<grid, 256, 0, (cudaStream_t)stream>>>(base, s1, s2, s2_limit, matched, n);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SNP_OK;
+} SNP_ABI_CATCH
+
 int snp_crc32c_batch(snp_ctx *c, const uint8_t *base, const uint64_t *off, const uint32_t *len, uint32_t *crc,
                      size_t n, int masked, int mem_kind, void *stream) try {
     if (mem_kind != SNP_MEM_HOST && mem_kind != SNP_MEM_DEVICE) return SNP_E_INVALID_ARG;
@@ -1230,59 +1260,110 @@ int snp_frame_compress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, si
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    cudaStream_t s = c->stream;
-    const size_t nch = (n + SNP_BLOCK_SIZE - 1) / SNP_BLOCK_SIZE;
-    const size_t pitch = (size_t)snp_get_max_compressed_length(SNP_BLOCK_SIZE);
-    MetaLayout ml(nch);
-    const size_t extra = 2 * align_up(nch * 4, 256) + align_up(nch * 8, 256) + 256;  // crc, sizes, scan, total
-    if ((rc = c->d_in.reserve(n + 16))) return rc;
-    if ((rc = c->d_tmp.reserve(nch * pitch))) return rc;
-    if ((rc = c->d_meta.reserve(ml.bytes + extra))) return rc;
-    uint8_t *dm = (uint8_t *)c->d_meta.p;
-    std::vector<uint64_t> off(nch), slot(nch);
-    std::vector<uint32_t> len(nch), capv(nch, (uint32_t)pitch);
-    for (size_t f = 0; f < nch; f++) {
-        off[f] = f * (uint64_t)SNP_BLOCK_SIZE;
-        slot[f] = f * pitch;
-        len[f] = (uint32_t)std::min<size_t>(n - off[f], SNP_BLOCK_SIZE);
+    for (auto &sl : c->slots) {
+        if (!sl.stream) CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (!sl.meta_ready) CU(cudaEventCreateWithFlags(&sl.meta_ready, cudaEventDisableTiming));
     }
-    CU(cudaMemcpyAsync(dm + ml.in_off, off.data(), nch * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(dm + ml.out_off, slot.data(), nch * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(dm + ml.in_len, len.data(), nch * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(dm + ml.out_cap, capv.data(), nch * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, s));
-    auto *d_raw_off = (const uint64_t *)(dm + ml.in_off);
-    auto *d_raw_len = (const uint32_t *)(dm + ml.in_len);
-    auto *d_comp_len = (uint32_t *)(dm + ml.out_len);
-    auto *d_status = (int32_t *)(dm + ml.status);
-    auto *d_crc = (uint32_t *)(dm + ml.bytes);
-    auto *d_sizes = (uint32_t *)(dm + ml.bytes + align_up(nch * 4, 256));
-    auto *d_scan = (uint64_t *)(dm + ml.bytes + 2 * align_up(nch * 4, 256));
-    auto *d_total = (uint64_t *)(dm + ml.bytes + 2 * align_up(nch * 4, 256) + align_up(nch * 8, 256));
-    // every chunk is an independent Snappy.Compress (SnappyStreamCompressor.cs:206)
-    rc = launch_compress(c, s, (const uint8_t *)c->d_in.p, d_raw_off, d_raw_len, (uint8_t *)c->d_tmp.p,
-                         (const uint64_t *)(dm + ml.out_off), (const uint32_t *)(dm + ml.out_cap), d_comp_len,
-                         d_status, nch, hash_mode, 0);
-    if (rc) return rc;
-    unsigned grid = (unsigned)std::min((nch + 7) / 8, (size_t)c->sm_count * 8);
-    snp::k_crc32c_masked_batch<<<grid, 256, 0, s>>>((const uint8_t *)c->d_in.p, d_raw_off, d_raw_len, d_crc, nch, 1);
-    snp::k_frame_plan<<<(unsigned)((nch + 255) / 256), 256, 0, s>>>(d_raw_len, d_comp_len, d_sizes, nch);
-    k_frag_scan<<<1, 1024, 0, s>>>(d_sizes, d_status, d_scan, d_total, nch);
-    c->launches += 3;
-    uint64_t total_bad[2];
-    CU(cudaMemcpyAsync(total_bad, d_total, 16, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    const size_t total = 10 + (size_t)total_bad[0];
-    if (total > cap) return SNP_OUTPUT_TOO_SMALL;
-    if ((rc = c->d_out.reserve(total + 16))) return rc;
-    snp::k_frame_emit<<<(unsigned)std::min<size_t>(nch, 4096), 256, 0, s>>>(
-        (const uint8_t *)c->d_in.p, d_raw_off, d_raw_len, (const uint8_t *)c->d_tmp.p, pitch, d_comp_len, d_crc, d_scan,
-        (uint8_t *)c->d_out.p, nch);
-    c->launches++;
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, c->d_out.p, total, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    *written = total;
+    // The stream is cut into pieces of kPiece chunks that flow through the pipeline slots like the chunks of the batched
+    // host-mode calls: H2D of piece k+1 | compress + CRC + frame kernels of piece k | D2H of piece k-1.  The reference
+    // does the same thing one 64 KiB chunk at a time (SnappyStreamCompressor.cs:166-230).  A piece's framed bytes are
+    // dense in its slot's device buffer; its position in the caller's buffer is the running total of the pieces before it.
+    const size_t nch = (n + SNP_BLOCK_SIZE - 1) / SNP_BLOCK_SIZE;
+    // A piece's compress kernel lasts at least as long as its slowest block (tens of ms for dense-match data: one warp per
+    // block), so pieces must be large enough that the slots together hold a GPU-load of blocks: 4 x the copy-bound size.
+    const size_t kPiece = std::max<size_t>(1, c->host_comp_chunk_bytes / SNP_BLOCK_SIZE);
+    const size_t pitch = (size_t)snp_get_max_compressed_length(SNP_BLOCK_SIZE);
+    constexpr size_t kLag = snp_ctx::kSlots / 2;
+    struct Piece {
+        size_t f0, f1;  // chunk range
+        int slot;
+        size_t total_off;  // where the piece's total lands in the slot's pinned metadata
+    };
+    std::deque<Piece> pend;
+    size_t pos = 0;  // framed bytes handed to the caller so far
+    auto phase2 = [&](const Piece &pc) -> int {
+        snp_ctx::Slot &sl = c->slots[pc.slot];
+        CU(cudaEventSynchronize(sl.meta_ready));
+        const uint64_t *tb = (const uint64_t *)((const uint8_t *)sl.h_meta.p + pc.total_off);
+        const size_t total = (size_t)tb[0] + (pc.f0 == 0 ? 10 : 0);
+        if (pos + total > cap) return SNP_OUTPUT_TOO_SMALL;
+        CU(cudaMemcpyAsync(out + pos, sl.d_out.p, total, cudaMemcpyDeviceToHost, sl.stream));
+        pos += total;
+        return SNP_OK;
+    };
+    int k = 0;
+    for (size_t f0 = 0; f0 < nch && rc == SNP_OK; f0 += kPiece) {
+        Piece pc;
+        pc.f0 = f0;
+        pc.f1 = std::min(nch, f0 + kPiece);
+        pc.slot = k++ % snp_ctx::kSlots;
+        const size_t m = pc.f1 - pc.f0;
+        const size_t b0 = f0 * (size_t)SNP_BLOCK_SIZE, b1 = std::min(n, pc.f1 * (size_t)SNP_BLOCK_SIZE);
+        snp_ctx::Slot &sl = c->slots[pc.slot];
+        cudaStream_t s = sl.stream;
+        CU(cudaStreamSynchronize(s));  // the slot's previous piece is completely done
+        MetaLayout ml(m);
+        const size_t a4 = align_up(m * 4, 256), a8 = align_up(m * 8, 256);
+        const size_t o_crc = ml.bytes, o_sizes = o_crc + a4, o_scan = o_sizes + a4, o_total = o_scan + a8;
+        pc.total_off = o_total;
+        if ((rc = sl.d_in.reserve(b1 - b0 + 16))) break;
+        if ((rc = sl.d_tmp.reserve(m * pitch))) break;
+        if ((rc = sl.d_out.reserve(b1 - b0 + 8 * m + 32))) break;  // every chunk may fall back to raw
+        if ((rc = sl.d_meta.reserve(o_total + 256))) break;
+        if ((rc = sl.h_meta.reserve(o_total + 256))) break;
+        uint8_t *dm = (uint8_t *)sl.d_meta.p, *hm = (uint8_t *)sl.h_meta.p;
+        {
+            uint64_t *ri = (uint64_t *)(hm + ml.in_off), *ro = (uint64_t *)(hm + ml.out_off);
+            uint32_t *rl = (uint32_t *)(hm + ml.in_len), *rc_ = (uint32_t *)(hm + ml.out_cap);
+            for (size_t i = 0; i < m; i++) {
+                ri[i] = i * (uint64_t)SNP_BLOCK_SIZE;
+                ro[i] = i * pitch;
+                rl[i] = (uint32_t)std::min<size_t>(b1 - b0 - ri[i], SNP_BLOCK_SIZE);
+                rc_[i] = (uint32_t)pitch;
+            }
+        }
+        CU(cudaMemcpyAsync(dm, hm, ml.out_len, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(sl.d_in.p, in + b0, b1 - b0, cudaMemcpyHostToDevice, s));
+        auto *d_raw_off = (const uint64_t *)(dm + ml.in_off);
+        auto *d_raw_len = (const uint32_t *)(dm + ml.in_len);
+        auto *d_comp_len = (uint32_t *)(dm + ml.out_len);
+        auto *d_status = (int32_t *)(dm + ml.status);
+        auto *d_crc = (uint32_t *)(dm + o_crc);
+        auto *d_sizes = (uint32_t *)(dm + o_sizes);
+        auto *d_scan = (uint64_t *)(dm + o_scan);
+        auto *d_total = (uint64_t *)(dm + o_total);
+        // every chunk is an independent Snappy.Compress (SnappyStreamCompressor.cs:206)
+        rc = launch_compress(c, s, (const uint8_t *)sl.d_in.p, d_raw_off, d_raw_len, (uint8_t *)sl.d_tmp.p,
+                             (const uint64_t *)(dm + ml.out_off), (const uint32_t *)(dm + ml.out_cap), d_comp_len, d_status, m,
+                             hash_mode, 0, &sl.d_tables);
+        if (rc) break;
+        const unsigned grid = (unsigned)std::min((m + 7) / 8, (size_t)c->sm_count * 8);
+        snp::k_crc32c_masked_batch<<<grid, 256, 0, s>>>((const uint8_t *)sl.d_in.p, d_raw_off, d_raw_len, d_crc, m, 1);
+        snp::k_frame_plan<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(d_raw_len, d_comp_len, d_sizes, m);
+        k_frag_scan<<<1, 1024, 0, s>>>(d_sizes, d_status, d_scan, d_total, m);
+        snp::k_frame_emit<<<(unsigned)std::min<size_t>(m, 4096), 256, 0, s>>>(
+            (const uint8_t *)sl.d_in.p, d_raw_off, d_raw_len, (const uint8_t *)sl.d_tmp.p, pitch, d_comp_len, d_crc, d_scan,
+            (uint8_t *)sl.d_out.p, m, f0 == 0 ? 10u : 0u);
+        c->launches += 4;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(hm + o_total, d_total, 16, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(sl.meta_ready, s));
+        pend.push_back(pc);
+        if (pend.size() > kLag) {
+            rc = phase2(pend.front());
+            pend.pop_front();
+        }
+    }
+    while (rc == SNP_OK && !pend.empty()) {
+        rc = phase2(pend.front());
+        pend.pop_front();
+    }
+    for (auto &sl : c->slots) {
+        cudaError_t e = cudaStreamSynchronize(sl.stream);
+        if (e != cudaSuccess && rc == SNP_OK) rc = cuda_fail(e, "cudaStreamSynchronize(slot)", __LINE__);
+    }
+    if (rc != SNP_OK) return rc;
+    *written = pos;
     return SNP_OK;
 } SNP_ABI_CATCH
 
@@ -1353,73 +1434,139 @@ int snp_frame_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap, 
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard g(c->device);
-    cudaStream_t s = c->stream;
-    MetaLayout ml(nch);
-    const size_t extra = align_up(nch * 4, 256);  // crc
-    if ((rc = c->d_in.reserve(n + 16))) return rc;
-    if ((rc = c->d_out.reserve(total + 16))) return rc;
-    if ((rc = c->d_meta.reserve(ml.bytes + extra))) return rc;
-    uint8_t *dm = (uint8_t *)c->d_meta.p;
-    // batch A: the compressed chunks (decode);  arrays B: every chunk's output region (CRC)
-    std::vector<uint64_t> a_in, a_out, b_off(nch);
-    std::vector<uint32_t> a_len, a_cap, b_len(nch);
-    std::vector<size_t> a_idx;
-    uint64_t op = 0;
-    for (size_t i = 0; i < nch; i++) {
-        b_off[i] = op;
-        b_len[i] = chunks[i].ulen;
-        if (chunks[i].type == 0x00) {
-            a_in.push_back(chunks[i].body), a_len.push_back(chunks[i].len);
-            a_out.push_back(op), a_cap.push_back(chunks[i].ulen), a_idx.push_back(i);
+    for (auto &sl : c->slots) {
+        if (!sl.stream) CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (!sl.meta_ready) CU(cudaEventCreateWithFlags(&sl.meta_ready, cudaEventDisableTiming));
+    }
+    // Pieces of consecutive chunks flow through the pipeline slots: H2D of the piece's byte span | decode of its
+    // compressed chunks + copies of its raw chunks + CRC32C of every chunk's output | D2H of the piece's output (enqueued
+    // right behind the kernels: like the reference, which hands chunk after chunk to the caller before it meets a bad one,
+    // SnappyStreamDecompressor.cs:38-208).  Statuses and CRCs are checked kLag pieces later, in stream order.
+    constexpr size_t kLag = snp_ctx::kSlots / 2;
+    struct Piece {
+        size_t f0, f1, na;
+        int slot;
+        size_t o_aout, o_crc;  // offsets of the decode results / CRCs in the slot's pinned metadata
+    };
+    std::deque<Piece> pend;
+    int verdict = SNP_OK;
+    auto phase2 = [&](const Piece &pc) -> int {  // returns a call-level error; a bad chunk goes to `verdict`
+        snp_ctx::Slot &sl = c->slots[pc.slot];
+        CU(cudaEventSynchronize(sl.meta_ready));
+        if (verdict != SNP_OK) return SNP_OK;
+        const uint8_t *hm = (const uint8_t *)sl.h_meta.p;
+        MetaLayout ml(pc.f1 - pc.f0);
+        const int32_t *a_st = (const int32_t *)(hm + ml.status);
+        const uint32_t *crc = (const uint32_t *)(hm + pc.o_crc);
+        size_t ai = 0;
+        for (size_t i = pc.f0; i < pc.f1; i++) {  // first bad chunk in stream order decides (the reference throws there)
+            if (chunks[i].type == 0x00 && a_st[ai++] != SNP_OK) {
+                verdict = a_st[ai - 1];
+                return SNP_OK;
+            }
+            if (crc[i - pc.f0] != chunks[i].crc) {
+                verdict = SNP_CRC_MISMATCH;
+                return SNP_OK;
+            }
         }
-        op += chunks[i].ulen;
-    }
-    const size_t na = a_idx.size();
-    CU(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, s));
-    if (na) {
-        CU(cudaMemcpyAsync(dm + ml.in_off, a_in.data(), na * 8, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(dm + ml.out_off, a_out.data(), na * 8, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(dm + ml.in_len, a_len.data(), na * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(dm + ml.out_cap, a_cap.data(), na * 4, cudaMemcpyHostToDevice, s));
-        rc = launch_decompress(c, s, (const uint8_t *)c->d_in.p, (const uint64_t *)(dm + ml.in_off),
-                               (const uint32_t *)(dm + ml.in_len), (uint8_t *)c->d_out.p,
-                               (const uint64_t *)(dm + ml.out_off), (const uint32_t *)(dm + ml.out_cap),
-                               (uint32_t *)(dm + ml.out_len), (int32_t *)(dm + ml.status), na);
-        if (rc) return rc;
-    }
-    for (size_t i = 0; i < nch; i++)  // type 0x01: raw copy (SnappyStreamDecompressor.cs:137-178)
-        if (chunks[i].type == 0x01 && chunks[i].len)
-            CU(cudaMemcpyAsync((uint8_t *)c->d_out.p + b_off[i], (const uint8_t *)c->d_in.p + chunks[i].body,
-                               chunks[i].len, cudaMemcpyDeviceToDevice, s));
-    std::vector<uint32_t> a_olen(na);
-    std::vector<int32_t> a_st(na);
-    if (na) {
-        CU(cudaMemcpyAsync(a_olen.data(), dm + ml.out_len, na * 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(a_st.data(), dm + ml.status, na * 4, cudaMemcpyDeviceToHost, s));
-    }
-    CU(cudaStreamSynchronize(s));  // metadata of batch A consumed; reuse the arrays for the CRC batch
-    CU(cudaMemcpyAsync(dm + ml.in_off, b_off.data(), nch * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(dm + ml.in_len, b_len.data(), nch * 4, cudaMemcpyHostToDevice, s));
-    unsigned grid = (unsigned)std::min((nch + 7) / 8, (size_t)c->sm_count * 8);
-    snp::k_crc32c_masked_batch<<<grid, 256, 0, s>>>((const uint8_t *)c->d_out.p, (const uint64_t *)(dm + ml.in_off),
-                                                    (const uint32_t *)(dm + ml.in_len), (uint32_t *)(dm + ml.bytes),
-                                                    nch, 1);
-    c->launches++;
-    CU(cudaGetLastError());
-    std::vector<uint32_t> crc(nch);
-    CU(cudaMemcpyAsync(crc.data(), dm + ml.bytes, nch * 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    // first bad chunk in stream order decides (the reference throws there)
-    size_t ai = 0;
-    for (size_t i = 0; i < nch; i++) {
-        if (chunks[i].type == 0x00) {
-            if (a_st[ai] != SNP_OK) return a_st[ai];
-            ai++;
+        return SNP_OK;
+    };
+    const uint64_t kSpan = c->host_chunk_bytes;
+    uint64_t opos = 0;
+    int k = 0;
+    size_t f0 = 0;
+    while (f0 < nch && rc == SNP_OK && verdict == SNP_OK) {
+        Piece pc;
+        pc.f0 = f0;
+        size_t f1 = f0;
+        uint64_t osz = 0;
+        const uint64_t ilo = chunks[f0].body;
+        while (f1 < nch && f1 - f0 < 16384) {
+            const uint64_t ihi = chunks[f1].body + chunks[f1].len;
+            if (f1 > f0 && (ihi - ilo > kSpan || osz + chunks[f1].ulen > kSpan)) break;
+            osz += chunks[f1].ulen;
+            f1++;
         }
-        if (crc[i] != chunks[i].crc) return SNP_CRC_MISMATCH;
+        pc.f1 = f1;
+        pc.slot = k++ % snp_ctx::kSlots;
+        const size_t m = f1 - f0;
+        const uint64_t ihi = chunks[f1 - 1].body + chunks[f1 - 1].len;
+        snp_ctx::Slot &sl = c->slots[pc.slot];
+        cudaStream_t s = sl.stream;
+        CU(cudaStreamSynchronize(s));  // the slot's previous piece is completely done
+        MetaLayout ml(m);
+        const size_t a4 = align_up(m * 4, 256), a8 = align_up(m * 8, 256);
+        const size_t o_boff = ml.bytes, o_blen = o_boff + a8, o_crc = o_blen + a4, o_end = o_crc + a4;
+        pc.o_aout = ml.out_len;
+        pc.o_crc = o_crc;
+        if ((rc = sl.d_in.reserve(ihi - ilo + 16))) break;
+        if ((rc = sl.d_out.reserve(osz + 16))) break;
+        if ((rc = sl.d_meta.reserve(o_end))) break;
+        if ((rc = sl.h_meta.reserve(o_end))) break;
+        uint8_t *dm = (uint8_t *)sl.d_meta.p, *hm = (uint8_t *)sl.h_meta.p;
+        size_t na = 0;
+        {
+            uint64_t *a_in = (uint64_t *)(hm + ml.in_off), *a_out = (uint64_t *)(hm + ml.out_off);
+            uint32_t *a_len = (uint32_t *)(hm + ml.in_len), *a_cap = (uint32_t *)(hm + ml.out_cap);
+            uint64_t *b_off = (uint64_t *)(hm + o_boff);
+            uint32_t *b_len = (uint32_t *)(hm + o_blen);
+            uint64_t op = 0;
+            for (size_t i = f0; i < f1; i++) {
+                b_off[i - f0] = op;
+                b_len[i - f0] = chunks[i].ulen;
+                if (chunks[i].type == 0x00) {
+                    a_in[na] = chunks[i].body - ilo, a_len[na] = chunks[i].len;
+                    a_out[na] = op, a_cap[na] = chunks[i].ulen;
+                    na++;
+                }
+                op += chunks[i].ulen;
+            }
+        }
+        pc.na = na;
+        CU(cudaMemcpyAsync(dm, hm, ml.out_len, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(dm + o_boff, hm + o_boff, a8 + a4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(sl.d_in.p, in + ilo, ihi - ilo, cudaMemcpyHostToDevice, s));
+        if (na) {
+            rc = launch_decompress(c, s, (const uint8_t *)sl.d_in.p, (const uint64_t *)(dm + ml.in_off),
+                                   (const uint32_t *)(dm + ml.in_len), (uint8_t *)sl.d_out.p,
+                                   (const uint64_t *)(dm + ml.out_off), (const uint32_t *)(dm + ml.out_cap),
+                                   (uint32_t *)(dm + ml.out_len), (int32_t *)(dm + ml.status), na);
+            if (rc) break;
+        }
+        {
+            const uint64_t *b_off = (const uint64_t *)(hm + o_boff);
+            for (size_t i = f0; i < f1; i++)  // type 0x01: raw copy (SnappyStreamDecompressor.cs:137-178)
+                if (chunks[i].type == 0x01 && chunks[i].len)
+                    CU(cudaMemcpyAsync((uint8_t *)sl.d_out.p + b_off[i - f0], (const uint8_t *)sl.d_in.p + (chunks[i].body - ilo),
+                                       chunks[i].len, cudaMemcpyDeviceToDevice, s));
+        }
+        const unsigned grid = (unsigned)std::min((m + 7) / 8, (size_t)c->sm_count * 8);
+        snp::k_crc32c_masked_batch<<<grid, 256, 0, s>>>((const uint8_t *)sl.d_out.p, (const uint64_t *)(dm + o_boff),
+                                                        (const uint32_t *)(dm + o_blen), (uint32_t *)(dm + o_crc), m, 1);
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(hm + ml.out_len, dm + ml.out_len, ml.bytes - ml.out_len, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(hm + o_crc, dm + o_crc, a4, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(sl.meta_ready, s));
+        if (osz) CU(cudaMemcpyAsync(out + opos, sl.d_out.p, osz, cudaMemcpyDeviceToHost, s));
+        opos += osz;
+        pend.push_back(pc);
+        if (pend.size() > kLag) {
+            rc = phase2(pend.front());
+            pend.pop_front();
+        }
+        f0 = f1;
     }
-    if (total) CU(cudaMemcpyAsync(out, c->d_out.p, total, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    while (rc == SNP_OK && !pend.empty()) {
+        rc = phase2(pend.front());
+        pend.pop_front();
+    }
+    for (auto &sl : c->slots) {
+        cudaError_t e = cudaStreamSynchronize(sl.stream);
+        if (e != cudaSuccess && rc == SNP_OK) rc = cuda_fail(e, "cudaStreamSynchronize(slot)", __LINE__);
+    }
+    if (rc != SNP_OK) return rc;
+    if (verdict != SNP_OK) return verdict;
     *written = (size_t)total;
     return SNP_OK;
 } SNP_ABI_CATCH

@@ -126,12 +126,13 @@ __global__ void k_frame_plan(const uint32_t *__restrict__ raw_len, const uint32_
     sizes[i] = 8 + payload;
 }
 
-// One CTA per chunk (grid-stride): header + payload at out + 10 + scan[i].
+// One CTA per chunk (grid-stride): header + payload at out + lead + scan[i].  lead = 10: this piece opens the stream and
+// starts with the stream identifier; lead = 0: a later piece of the same stream.
 __global__ void k_frame_emit(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ raw_off,
                              const uint32_t *__restrict__ raw_len, const uint8_t *__restrict__ comp, size_t pitch,
                              const uint32_t *__restrict__ comp_len, const uint32_t *__restrict__ crc,
-                             const uint64_t *__restrict__ scan, uint8_t *__restrict__ out, size_t n) {
-    if (blockIdx.x == 0 && threadIdx.x < 10) {  // stream identifier (SnappyStreamCompressor.cs:15-18)
+                             const uint64_t *__restrict__ scan, uint8_t *__restrict__ out, size_t n, uint32_t lead) {
+    if (lead && blockIdx.x == 0 && threadIdx.x < 10) {  // stream identifier (SnappyStreamCompressor.cs:15-18)
         const uint8_t id[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};
         out[threadIdx.x] = id[threadIdx.x];
     }
@@ -139,7 +140,7 @@ __global__ void k_frame_emit(const uint8_t *__restrict__ raw, const uint64_t *__
         const bool compressed = comp_len[i] < raw_len[i];
         const uint32_t payload = compressed ? comp_len[i] : raw_len[i];
         const uint8_t *src = compressed ? comp + i * pitch : raw + raw_off[i];
-        uint8_t *d = out + 10 + scan[i];
+        uint8_t *d = out + lead + scan[i];
         if (threadIdx.x < 8) {
             const uint32_t size24 = payload + 4;  // + CRC
             const uint32_t c = crc[i];

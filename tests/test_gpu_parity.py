@@ -572,3 +572,111 @@ def test_pack_batch_matches_concatenation(engine):
         got = dst.cpu().numpy()
         assert got[16:16 + len(want)].tobytes() == want
         assert (got[:16] == 0xEE).all() and (got[16 + len(want):] == 0xEE).all()
+
+
+def test_find_match_length_kats_on_the_gpu(engine, kats):
+    """The 45 known-answer vectors of SnappyCompressorTests.cs:10-81, run through the compress kernels' own device
+    function (snp_find_match_length_batch) -- not only through whole-fragment parity."""
+    import torch
+    dev = torch.device("cuda", 0)
+    buf, s1, s2, lim, want = bytearray(), [], [], [], []
+    for k in kats["find_match_length"]:
+        a, b, length = k["s1"].encode(), k["s2"].encode(), k["length"]
+        while len(buf) % 4 != len(want) % 4:  # every alignment of the pair
+            buf += b"\xee"
+        s1.append(len(buf))
+        buf += a
+        s2.append(len(buf))
+        buf += b + b"\0" * max(0, length - len(b))
+        lim.append(s2[-1] + length)
+        want.append(k["expected"])
+        buf += b"\xdd" * 7
+    assert len(want) == 45
+    t = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+    got = engine.find_match_length_batch_device(torch.tensor(list(buf) + [0] * 64, dtype=torch.uint8, device=dev), t(s1), t(s2), t(lim))
+    torch.cuda.synchronize()
+    assert got.cpu().tolist() == want
+
+
+def _random_data_inputs(seed: int, count: int, big: int):
+    """The input distribution of SnappyTests.cs:401-446 (RandomData): the first `big` inputs are 64..128 KiB of runs of
+    arbitrary bytes, the rest 0..4 KiB of runs over a skewed small alphabet; run lengths skewed short."""
+    rng = np.random.default_rng(seed)
+    res = []
+    for i in range(count):
+        length = int(rng.integers(0, 4095)) if i >= big else 65536 + int(rng.integers(0, 65535))
+        out = bytearray()
+        while len(out) < length:
+            run = 1
+            if rng.integers(0, 9) == 0:
+                run = int(rng.integers(0, max(1, (1 << int(rng.integers(0, 8))) - 1)))
+            c = int(rng.integers(0, 255))
+            if i >= big:
+                c = int(rng.integers(0, max(1, (1 << int(rng.integers(0, 3))) - 1)))
+            out += bytes([c]) * run
+        res.append(bytes(out[:length]))
+    return res
+
+
+@pytest.mark.parametrize("kernel", ["7", "8"])
+def test_random_data_distribution_round_trips(oracle, kernel):
+    """SnappyTests.cs:401-446 on the GPU: 2 100 inputs of the RandomData distribution (100 above 64 KiB, through the
+    single-call API with its fragment loop; 2 000 small ones as one batch), compressed bit-exactly like the oracle and
+    decompressed back by the default and by the challenger decompress kernel."""
+    from snappier_b200 import snappy as S
+    from snappier_b200.batch import compress_many, decompress_many
+    eng = _engine_with({"SNP_DECOMP_KERNEL": kernel})
+    inputs = _random_data_inputs(301, 2100, 100)
+    small = inputs[100:]
+    comp, st = compress_many(eng, small, 0)
+    assert not st.any()
+    for i in range(0, len(small), 7):
+        assert comp[i] == oracle.compress(small[i])[1], i
+    back, st = decompress_many(eng, comp)
+    assert not st.any() and back == small
+    for d in inputs[:100:9]:  # multi-fragment inputs (Snappy.CompressToMemory / DecompressToMemory)
+        c = S.compress_to_array(d)
+        assert c == oracle.compress(d)[1]
+        assert S.decompress_to_array(c) == d
+    big_comp = [oracle.compress(d)[1] for d in inputs[:100]]
+    back, st = decompress_many(eng, big_comp)  # > 64 KiB under one header, batched
+    assert not st.any() and back == inputs[:100]
+    eng.close()
+
+
+@pytest.mark.parametrize("kernel", ["7", "8"])
+def test_decode_at_scale_streams_the_engine_did_not_produce(oracle, kernel):
+    """2^14 blocks of bench.py's config-2 mixture compressed by the ORACLE (both hash modes) and by Google's encoder
+    (pyarrow) -- not by the engine's own compressor -- decode bit-exactly in one batched call."""
+    import torch
+    import bench as B
+    pa = pytest.importorskip("pyarrow")
+    codec = pa.Codec("snappy")
+    n = 1 << 14
+    corpus = {k: torch.from_numpy(v) for k, v in B.load_corpus().items()}
+    raw = torch.cat([B.make_blocks(torch, corpus, b0, 4096, torch.device("cpu")) for b0 in range(0, n, 4096)]).numpy()
+    r_off = np.arange(n, dtype=np.uint64) * B.BLOCK
+    r_len = np.full(n, B.BLOCK, np.uint32)
+    s_off = np.arange(n, dtype=np.uint64) * B.PITCH
+    s_cap = np.full(n, B.PITCH, np.uint32)
+    eng = _engine_with({"SNP_DECOMP_KERNEL": kernel})
+    for producer in ("oracle-crc32c", "oracle-mul", "google"):
+        slots = np.zeros(n * B.PITCH, np.uint8)
+        if producer == "google":
+            lens = np.zeros(n, np.uint32)
+            for i in range(0, n, 4):  # every 4th block through pyarrow (one thread), the rest left empty
+                c = codec.compress(raw[i].tobytes()).to_pybytes()
+                slots[i * B.PITCH: i * B.PITCH + len(c)] = np.frombuffer(c, np.uint8)
+                lens[i] = len(c)
+            sel = np.arange(0, n, 4)
+        else:
+            bad, lens, _ = oracle.compress_batch(raw.reshape(-1), r_off, r_len, slots, s_off, s_cap,
+                                                 0 if producer == "oracle-crc32c" else 1, 8)
+            assert bad == 0
+            sel = np.arange(n)
+        out = np.zeros(len(sel) * B.BLOCK, np.uint8)
+        ol, st = eng.decompress_batch_host(slots, s_off[sel], lens[sel], out, np.arange(len(sel), dtype=np.uint64) * B.BLOCK,
+                                           np.full(len(sel), B.BLOCK, np.uint32))
+        assert not st.any() and (ol == B.BLOCK).all(), producer
+        assert np.array_equal(out.reshape(len(sel), B.BLOCK), raw[sel]), producer
+    eng.close()

@@ -15,8 +15,13 @@ import bench as B  # noqa: E402
 import class_bench as CB  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+kind = sys.argv[2] if len(sys.argv) > 2 else "config3"
 dev = torch.device("cuda", 0)
-raw = torch.cat([B.make_blocks_config3(torch, b0, min(8192, n - b0), dev) for b0 in range(0, n, 8192)]).view(-1)
+if kind == "config3":
+    raw = torch.cat([B.make_blocks_config3(torch, b0, min(8192, n - b0), dev) for b0 in range(0, n, 8192)]).view(-1)
+else:
+    corpus_dev = {k: torch.from_numpy(v).to(dev) for k, v in B.load_corpus().items()}
+    raw = torch.cat([B.make_blocks(torch, corpus_dev, b0, min(8192, n - b0), dev) for b0 in range(0, n, 8192)]).view(-1)
 h_raw = torch.empty(n * B.BLOCK, dtype=torch.uint8).pin_memory()
 h_raw.copy_(raw)
 h_slots = torch.empty(n * B.PITCH, dtype=torch.uint8).pin_memory()
@@ -26,7 +31,7 @@ s_off = np.arange(n, dtype=np.uint64) * B.PITCH
 s_cap = np.full(n, B.PITCH, np.uint32)
 ref = None
 for mb in (64, 128, 256, 512):
-    eng = CB.engine_with({"SNP_HOST_CHUNK_MB": str(mb)})
+    eng = CB.engine_with({"SNP_HOST_COMP_CHUNK_MB": str(mb)})
     for _ in range(2):
         eng.compress_batch_host(h_raw.numpy(), r_off, r_len, h_slots.numpy(), s_off, s_cap, 0)
     torch.cuda.synchronize()
@@ -36,5 +41,5 @@ for mb in (64, 128, 256, 512):
     dt = (time.perf_counter() - t0) / 4
     tot = int(ol.astype(np.int64).sum())
     ref = ref or tot
-    print(f"chunk {mb:4d} MiB: {n * B.BLOCK / dt / 1e9:6.2f} GB/s  ok={not st.any() and tot == ref}", flush=True)
+    print(f"{kind} chunk {mb:4d} MiB: {n * B.BLOCK / dt / 1e9:6.2f} GB/s  ok={not st.any() and tot == ref}", flush=True)
     eng.close()
