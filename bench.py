@@ -785,6 +785,13 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # N > 1: every rank works from the CPUs / memory of the NUMA node its GPU hangs off (the e2e legs copy from and to
+    # pinned host buffers; unbound, the ranks' PCIe streams cross the socket interconnect).  Not at N = 1: the host-core
+    # baseline of that run must see all the cores.
+    numa_info = None
+    if world > 1 and os.environ.get("SNP_BENCH_NUMA", "1") != "0":
+        from snappier_b200 import numa
+        numa_info = numa.bind_to_gpu_node(local)
     engine = Engine(local)
     n = args.blocks
     if args.workload == "compress":
@@ -915,6 +922,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
         }
+        if numa_info is not None:
+            line["numa"] = numa_info
 
     # ---- the other half of BASELINE's metric (config 3) and, across GPUs, config 5: same JSON line ----
     del comp, out, h_in, h_out, np_in, np_out
