@@ -412,16 +412,15 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
         const bool far = mine && is_copy && off > NEAR_MAX;
         const bool staged = far && len <= 16u;
         const uint32_t gsrc = wxd - off;  // window coordinate of the source
-        if (__any_sync(SNP_FULL, staged)) {
+        // (the loads are issued here and stored below, behind the descriptor arithmetic: that much of their latency is free)
+        const bool any_staged = __any_sync(SNP_FULL, staged);
+        const uint32_t nw = staged ? ((gsrc & 3u) + len + 3u) >> 2 : 0u;
+        uint32_t w[SNP7_STAGE_W];
+        if (any_staged) {
             const uint32_t *gp = reinterpret_cast<const uint32_t *>(out16 + (gsrc & ~3u));
-            const uint32_t nw = staged ? ((gsrc & 3u) + len + 3u) >> 2 : 0u;
-            uint32_t w[SNP7_STAGE_W];
 #pragma unroll
             for (uint32_t j = 0; j < SNP7_STAGE_W; j++)
                 if (j < nw) w[j] = gp[j];
-#pragma unroll
-            for (uint32_t j = 0; j < SNP7_STAGE_W; j++)
-                if (j < nw) s->stage[lane * SNP7_STAGE_W + j] = w[j];
         }
         // descriptor of my tag for the rounds (t = wx + descriptor; only the low 16 bits of the sum are used):
         //   literal / staged far copy: shared-memory byte (t & 0xffff), a linear address inside Warp7;
@@ -439,6 +438,11 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
         if (__any_sync(SNP_FULL, close)) {
             const uint32_t r0 = (dst - op) >> 5, r1 = (dst + len - 1u - op) >> 5;
             slow_rounds = __reduce_or_sync(SNP_FULL, close ? (2u << r1) - (1u << r0) : 0u);
+        }
+        if (any_staged) {
+#pragma unroll
+            for (uint32_t j = 0; j < SNP7_STAGE_W; j++)
+                if (j < nw) s->stage[lane * SNP7_STAGE_W + j] = w[j];
         }
         __syncwarp();  // the staged words are visible to every lane
 

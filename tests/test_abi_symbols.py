@@ -79,3 +79,12 @@ def test_product_path_never_imports_oracle():
                     for pat in (r'#\s*include\s*[<"][^>"]*oracle', r'^\s*(from|import)\s+oracle', r'\borc_\w+\s*\(',
                                 r'libsnappy_oracle', r'pyoracle', r'dlopen[^\n]*oracle'):
                         assert not re.search(pat, txt, re.M), (f, pat)  # doc comments may cite oracle/ by path
+
+
+def test_numa_helper_parses_cpulists_and_is_a_noop_without_sysfs():
+    """snappier_b200.numa: cpulist parsing, and binding degrades to a no-op where the GPU's node is unknown."""
+    from snappier_b200 import numa
+    assert numa._parse_cpulist("0-3,8,10-11") == [0, 1, 2, 3, 8, 10, 11]
+    assert numa._parse_cpulist("5") == [5]
+    info = numa.bind_to_gpu_node(0)  # no GPU here: nothing may change
+    assert info["bound"] is False and info["cpus"] >= 1

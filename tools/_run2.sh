@@ -1,4 +1,8 @@
 mkdir -p gpurun_out
-timeout 900 python tools/e2e_compress_probe.py 65536 config3 > gpurun_out/r02_e2e_compress.log 2>&1; cat gpurun_out/r02_e2e_compress.log
-timeout 900 python tools/e2e_compress_probe.py 65536 mix > gpurun_out/r02_e2e_compress_mix.log 2>&1; cat gpurun_out/r02_e2e_compress_mix.log
-timeout 900 python bench.py --workload frame --steps 3 --frame-gib 4 > gpurun_out/r02_bench_frame.json 2> gpurun_out/r02_bench_frame.err; tail -3 gpurun_out/r02_bench_frame.err; cat gpurun_out/r02_bench_frame.json | cut -c1-200; grep -o '"frame_compress_GBps[^,]*,[^,]*' gpurun_out/r02_bench_frame.json
+timeout 900 python tools/class_bench.py --blocks 65536 --variants 7 --small "" --out gpurun_out/r02_class_bench8.json > gpurun_out/r02_class_bench8.log 2>&1
+cat gpurun_out/r02_class_bench8.log
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --decompress-only > gpurun_out/r02_bench_b.json 2> gpurun_out/r02_bench_b.err; tail -3 gpurun_out/r02_bench_b.err; python - <<'PY'
+import json
+j=json.loads(open('gpurun_out/r02_bench_b.json').read().strip().split('\n')[-1])
+print(j['value'], j['roofline']['frac'], j['e2e'])
+PY
