@@ -458,15 +458,16 @@ __device__ __noinline__ int decompress_block_v7(const uint8_t *__restrict__ in, 
             cm1 += __popc(M);
             const uint32_t t = wx + d;
             const uint32_t si = t & ((int32_t)d < 0 ? (W - 1) : 0xffffu);
-            const bool active = wx < wxe;
-            uint32_t v = 0;
             if (with_global) {
-                if (active && !(d & D_GLOBAL)) v = sb[si];
-                if (active && (d & D_GLOBAL)) v = out16[wx - (d & 0xffffu)];
+                const bool glob = wx < wxe && (d & D_GLOBAL);
+                uint32_t v = sb[(wx < wxe && !glob) ? si : (wx & (W - 1))];  // lanes behind the group: self-copy (below)
+                if (glob) v = out16[wx - (d & 0xffffu)];
+                s->win[wx & (W - 1)] = (uint8_t)v;
             } else {
-                if (active) v = sb[si];
+                // branch-free: lanes behind the end of the group copy a (valid) window byte onto a window position that
+                // the next group overwrites -- < 32 bytes ahead of op, inside the 64 bytes of slack NEAR_MAX leaves
+                s->win[wx & (W - 1)] = sb[wx < wxe ? si : (wx & (W - 1))];
             }
-            if (active) s->win[wx & (W - 1)] = (uint8_t)v;
             wx += 32u;
             __syncwarp();
         };
