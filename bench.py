@@ -767,7 +767,7 @@ def main():
     ap.add_argument("--workload", default="decompress", choices=["decompress", "compress", "frame", "roundtrip"],
                     help="decompress = BASELINE config 2 (the headline); compress = config 3, frame = config 4, "
                          "roundtrip = config 5 (extra lines, not the driver's)")
-    ap.add_argument("--frame-gib", type=float, default=4.0, help="frame workload: stream size (config 4 names 16 GiB)")
+    ap.add_argument("--frame-gib", type=float, default=16.0, help="frame workload: stream size (config 4 names 16 GiB; needs 3x that of pinned host memory)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "handmade or golden_chunks or bad_data or pack_batch or find_match" > gpurun_out/r02_memcheck_v7.log 2>&1; echo "memcheck v7 rc=$?" >> gpurun_out/r02_memcheck_v7.log; tail -4 gpurun_out/r02_memcheck_v7.log
-SNP_DECOMP_KERNEL=8 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "handmade or golden_chunks or bad_data or copy4" > gpurun_out/r02_memcheck_v8.log 2>&1; echo "memcheck v8 rc=$?" >> gpurun_out/r02_memcheck_v8.log; tail -4 gpurun_out/r02_memcheck_v8.log
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "handmade or golden_chunks" > gpurun_out/r02_racecheck_v7.log 2>&1; echo "racecheck v7 rc=$?" >> gpurun_out/r02_racecheck_v7.log; tail -4 gpurun_out/r02_racecheck_v7.log
+free -g | head -2
+timeout 1500 python bench.py --workload frame --steps 2 --frame-gib 16 > gpurun_out/r02_bench_frame16.json 2> gpurun_out/r02_bench_frame16.err; tail -3 gpurun_out/r02_bench_frame16.err; cat gpurun_out/r02_bench_frame16.json | cut -c1-1200
