@@ -82,3 +82,47 @@ def _worker(rank: int, world: int, port: int, n_blocks: int):
 @pytest.mark.parametrize("world,n_blocks", [(2, 23), (3, 10), (2, 1)])
 def test_scatter_process_gather_round_trip(oracle, world, n_blocks):
     mp.spawn(_worker, args=(world, _free_port(), n_blocks), nprocs=world, join=True)
+
+
+def _subgroup_worker(rank: int, world: int, port: int, n_blocks: int):
+    """Scatter / gather inside a SUB-group whose ranks differ from the global ones (group {1, 2} of a 3-rank world: group
+    rank r is global rank r + 1): sharding.py must translate group ranks to the global ranks torch.distributed's
+    broadcast / point-to-point calls take."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from snappier_b200.batch import pack
+    try:
+        grp = dist.new_group(ranks=[1, 2])  # every rank calls new_group; only 1 and 2 are members
+        if rank in (1, 2):
+            g_rank = dist.get_rank(grp)
+            assert g_rank == rank - 1
+            blocks = [bytes([i % 251]) * (100 + 13 * i) for i in range(n_blocks)]
+            if g_rank == 0:
+                base, off, ln = pack(blocks)
+                t = (torch.from_numpy(base), torch.from_numpy(off.astype(np.int64)), torch.from_numpy(ln.astype(np.int32)))
+            else:
+                t = (None, None, None)
+            my_base, my_off, my_len, first, n_total = sharding.scatter_batch(*t, src=0, device=torch.device("cpu"), group=grp)
+            lo, hi = sharding.shard_range(n_blocks, 2, g_rank)
+            mb = my_base.numpy()
+            mine = [mb[int(o): int(o) + int(l)].tobytes() for o, l in zip(my_off, my_len)]
+            assert (first, n_total) == (lo, n_blocks) and mine == blocks[lo:hi]
+            # slots with slack, gathered to group rank 1 (= global rank 2)
+            slots = np.zeros(max(len(mine), 1) * 1024, np.uint8)
+            for i, b in enumerate(mine):
+                slots[i * 1024: i * 1024 + len(b)] = np.frombuffer(b, np.uint8)
+            g_base, g_off, g_len = sharding.gather_batch(torch.from_numpy(slots), torch.arange(len(mine), dtype=torch.int64) * 1024,
+                                                         torch.tensor([len(b) for b in mine], dtype=torch.int32), dst=1, group=grp)
+            if g_rank == 1:
+                gb = g_base.numpy()
+                assert [gb[int(o): int(o) + int(l)].tobytes() for o, l in zip(g_off, g_len)] == blocks
+            else:
+                assert g_base is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_scatter_gather_inside_a_subgroup():
+    mp.spawn(_subgroup_worker, args=(3, _free_port(), 9), nprocs=3, join=True)
