@@ -680,3 +680,31 @@ def test_decode_at_scale_streams_the_engine_did_not_produce(oracle, kernel):
         assert not st.any() and (ol == B.BLOCK).all(), producer
         assert np.array_equal(out.reshape(len(sel), B.BLOCK), raw[sel]), producer
     eng.close()
+
+
+def test_single_call_api_from_many_threads(oracle):
+    """The single-call API behind Snappy.Compress / Decompress is called from arbitrary thread-pool threads: all of them
+    share ONE default context per device (calls serialise on its mutex), results stay bit-exact and independent."""
+    import threading
+    from snappier_b200 import snappy as S
+    blocks = H.synthetic_blocks(909, 24, size=20000) + [b"", b"x", b"thread " * 5000]
+    want = [oracle.compress(b)[1] for b in blocks]
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(3):
+                for i in range(tid % 3, len(blocks), 3):
+                    c = S.compress_to_array(blocks[i])
+                    assert c == want[i], (tid, i)
+                    assert S.decompress_to_array(c) == blocks[i], (tid, i)
+                    assert S.get_uncompressed_length(c) == len(blocks[i])
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(12)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
