@@ -757,7 +757,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blocks", type=int, default=1 << 20, help="blocks per GPU (default 2^20 = BASELINE config 2)")
-    ap.add_argument("--e2e-blocks", type=int, default=1 << 15)
+    ap.add_argument("--e2e-blocks", type=int, default=1 << 16)
     ap.add_argument("--cpu-blocks", type=int, default=1 << 16)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-blocks", type=int, default=1 << 16)
