@@ -142,13 +142,21 @@ int snp_decompress_sequence(const uint8_t *const *seg_ptr, const size_t *seg_len
  * and reports out_len[i] (bytes produced; 0 unless status[i] == SNP_OK) and
  * status[i] (enum snp_status).  A bad item never affects its neighbours.
  * Item regions must not overlap each other or the input.
+ * CONTENT OF AN OUTPUT REGION BEYOND out_len[i] IS UNSPECIFIED: a batch call with
+ * two or more items may write anywhere inside [out_off[i], out_off[i] + out_cap[i])
+ * -- partial output of an item that is then rejected, or device scratch behind
+ * the produced bytes (host mode copies whole capacity spans back before the
+ * statuses are known; compress slots are copied as wide as the longest item of
+ * their group).  Callers that must not see such bytes clear the regions or use
+ * the single-call API, which leaves the output untouched on failure like the
+ * reference (it decodes into a private buffer).
  *
  * compress: in_len[i] <= SNP_BLOCK_SIZE (one fragment per item, one warp per
  *   item); give each item snp_get_max_compressed_length(in_len[i]) of capacity
  *   to make SNP_OUTPUT_TOO_SMALL impossible.  Larger inputs: snp_compress().
  * decompress: each item is a complete block with its own varint header.
  *
- * ctx == NULL uses the calling thread's default context.  `stream` is a
+ * ctx == NULL uses the process-wide default context of the calling thread's current device.  `stream` is a
  * cudaStream_t used for SNP_MEM_DEVICE only (NULL = the legacy default stream,
  * as everywhere in CUDA; the caller orders the work against its own).  Return: SNP_OK once the work is done (HOST) / enqueued (DEVICE),
  * or a negative snp_error.  Per-item failures are NOT a call failure. */
@@ -171,7 +179,8 @@ int snp_uncompressed_length_batch(snp_ctx *ctx, const uint8_t *in_base, const ui
  * What `new SnappyStream(s, CompressionMode.Compress)` emits for one Write of the whole buffer
  * followed by Dispose: stream identifier, then one chunk per 64 KiB
  * [type 0x00 | 0x01][len24][masked CRC32C of the raw chunk][snappy block | raw bytes]
- * (SnappyStreamCompressor.cs:15-18,166-261).  Host buffers, synchronous. */
+ * (SnappyStreamCompressor.cs:15-18,166-261).  Host buffers, synchronous; internally the stream flows through the
+ * host-mode pipeline in pieces of chunks (H2D | kernels | D2H overlap), as the reference processes it chunk by chunk. */
 
 /* 10 + n + 8 * ceil(n / 65536): every chunk falls back to raw when compression does not shrink it. */
 size_t snp_frame_max_compressed_length(size_t n);
