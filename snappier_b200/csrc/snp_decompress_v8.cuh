@@ -61,22 +61,7 @@ __device__ __forceinline__ void cp_async16_v8(void *smem_dst, const void *gsrc, 
 }
 __device__ __forceinline__ void cp_async_commit_v8() {}
 template <int N> __device__ __forceinline__ void cp_async_wait_v8() {}
-__device__ __forceinline__ uint64_t l2_policy_evict_first_v8() { return 0; }
-__device__ __forceinline__ void cp_async16_hint_v8(void *smem_dst, const void *gsrc, uint64_t) { memcpy(smem_dst, gsrc, 16); }
 #else
-// L2 eviction-priority policy for lines that are read once (far back-reference sources, the compressed stream): they
-// must not push the lanes' recently written output -- the target of most back-references -- out of L2
-__device__ __forceinline__ uint64_t l2_policy_evict_first_v8() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void cp_async16_hint_v8(void *smem_dst, const void *gsrc, uint64_t policy) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc), "l"(policy)
-                 : "memory");
-}
 // 16 bytes global -> shared, asynchronous; bytes past src_bytes are zero-filled (never read from memory)
 __device__ __forceinline__ void cp_async16_v8(void *smem_dst, const void *gsrc, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
@@ -93,7 +78,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait_v8() {
 // its region, bits 16..27 = byte offset of the region inside Lane8, bit 31 = the region is a 32-byte far buffer (no wrap).
 #define SNP8_FARBIT 0x80000000u
 
-template <uint32_t IR, uint32_t ORB, int D, int POL = 0>
+template <uint32_t IR, uint32_t ORB, int D>
 __device__ __forceinline__ void decompress_lanes_v8(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
                                                     const uint32_t *__restrict__ in_len, uint8_t *out_base,
                                                     const uint64_t *__restrict__ out_off,
@@ -111,7 +96,6 @@ __device__ __forceinline__ void decompress_lanes_v8(const uint8_t *__restrict__ 
     enum : uint32_t { RUN = 0, DRAIN_END = 1, DRAIN_BULK = 2, BULK_READY = 3 };
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
-    const uint64_t pol = POL ? l2_policy_evict_first_v8() : 0;
     uint8_t *const lb = reinterpret_cast<uint8_t *>(me);
     auto ldw = [&](uint32_t byte_off) -> uint32_t { return *reinterpret_cast<const uint32_t *>(lb + byte_off); };
 
@@ -406,13 +390,8 @@ __device__ __forceinline__ void decompress_lanes_v8(const uint8_t *__restrict__ 
                             } else {  // the source is in global memory already (older than anything in flight)
                                 if (p < rfrom) n = min(n, rfrom - p);  // the rest of the source sits in the ring: next step
                                 const uint8_t *g = out16 + (p & ~15u);
-                                if (POL) {
-                                    cp_async16_hint_v8(me->far[k], g, pol);
-                                    if ((p & 15u) + n > 16u) cp_async16_hint_v8(me->far[k] + 16, g + 16, pol);
-                                } else {
-                                    cp_async16_v8(me->far[k], g, 16u);
-                                    if ((p & 15u) + n > 16u) cp_async16_v8(me->far[k] + 16, g + 16, 16u);
-                                }
+                                cp_async16_v8(me->far[k], g, 16u);
+                                if ((p & 15u) + n > 16u) cp_async16_v8(me->far[k] + 16, g + 16, 16u);
                                 nd = SNP8_FARBIT | ((FOFF + 32u * k) << 16) | ((p & 15u) << 4) | n;
                             }
                             if (poff < Q && n == poff) poff <<= 1;  // a whole period appended: the pattern is twice as long
@@ -438,7 +417,7 @@ __device__ __forceinline__ void decompress_lanes_v8(const uint8_t *__restrict__ 
 }
 
 #ifndef SNP_EMU
-template <uint32_t IR, uint32_t ORB, int D, int NT, int CTAS, int POL = 0>  // ring bytes per lane, pipeline depth, threads per CTA, CTAs per SM, L2 policy
+template <uint32_t IR, uint32_t ORB, int D, int NT, int CTAS>  // ring bytes per lane, pipeline depth, threads per CTA, CTAs per SM
 __global__ void __launch_bounds__(NT, CTAS)
 k_decompress_v8(const uint8_t *__restrict__ in_base, const uint64_t *__restrict__ in_off,
                 const uint32_t *__restrict__ in_len, uint8_t *out_base, const uint64_t *__restrict__ out_off,
@@ -446,7 +425,7 @@ k_decompress_v8(const uint8_t *__restrict__ in_base, const uint64_t *__restrict_
                 size_t n_items, unsigned long long *__restrict__ next_item) {
     extern __shared__ __align__(16) uint8_t smem8[];
     Lane8<IR, ORB, D> *me = reinterpret_cast<Lane8<IR, ORB, D> *>(smem8) + threadIdx.x;
-    decompress_lanes_v8<IR, ORB, D, POL>(in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n_items,
+    decompress_lanes_v8<IR, ORB, D>(in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n_items,
                                  next_item, me);
 }
 #endif  // !SNP_EMU

@@ -152,13 +152,12 @@ int ctx_set_attrs(snp_ctx *c) {
     SNP7_ATTR(2048, 8, 5);
     SNP7_ATTR(4096, 8, 4);
 #undef SNP7_ATTR
-#define SNP8_ATTR(IR, ORB, D, NT, CTAS, ...)                                                                              \
-    CU(cudaFuncSetAttribute(snp::k_decompress_v8<IR, ORB, D, NT, CTAS, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+#define SNP8_ATTR(IR, ORB, D, NT, CTAS)                                                                              \
+    CU(cudaFuncSetAttribute(snp::k_decompress_v8<IR, ORB, D, NT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                             (int)(NT * sizeof(snp::Lane8<IR, ORB, D>))))
     SNP8_ATTR(128, 128, 3, 96, 6);
     SNP8_ATTR(128, 128, 3, 128, 4);
     SNP8_ATTR(128, 128, 4, 128, 4);
-    SNP8_ATTR(128, 128, 3, 96, 6, 1);
 #undef SNP8_ATTR
 
     c->attrs_set = true;
@@ -212,15 +211,14 @@ int launch_decompress(snp_ctx *c, cudaStream_t s, const uint8_t *in_base, const 
         if (rc) return rc;
         unsigned long long *ctr;
         if ((rc = ctx_work_counter(c, s, &ctr))) return rc;
-#define SNP8_LAUNCH(IR, ORB, D, NT, CTAS, ...)                                                                    \
+#define SNP8_LAUNCH(IR, ORB, D, NT, CTAS)                                                                         \
     do {                                                                                                          \
         const unsigned g8 = std::min((unsigned)((n + NT - 1) / NT), (unsigned)(c->sm_count * CTAS));              \
-        snp::k_decompress_v8<IR, ORB, D, NT, CTAS, ##__VA_ARGS__><<<g8, NT, NT * sizeof(snp::Lane8<IR, ORB, D>), s>>>( \
+        snp::k_decompress_v8<IR, ORB, D, NT, CTAS><<<g8, NT, NT * sizeof(snp::Lane8<IR, ORB, D>), s>>>(          \
             in_base, in_off, in_len, out_base, out_off, out_cap, out_len, status, n, ctr);                       \
     } while (0)
         if (c->v8_cfg == 1) SNP8_LAUNCH(128, 128, 3, 128, 4);       // 512 lanes per SM
         else if (c->v8_cfg == 2) SNP8_LAUNCH(128, 128, 4, 128, 4);  // deeper pipeline
-        else if (c->v8_cfg == 5) SNP8_LAUNCH(128, 128, 3, 96, 6, 1);  // 576 lanes, read-once lines evict first in L2
         else SNP8_LAUNCH(128, 128, 3, 96, 6);                       // 576 lanes per SM, 128-byte rings, depth 3
 #undef SNP8_LAUNCH
     } else if (kernel == 1)
@@ -923,12 +921,6 @@ int snp_create(int device, snp_ctx **out) try {
     c->decomp_kernel = env_int("SNP_DECOMP_KERNEL", 7);
     c->v7_window = env_int("SNP_V7_WINDOW", 4096);
     c->v8_cfg = env_int("SNP_V8_CFG", 0);
-    if (const int l2g = env_int("SNP_L2_FETCH", 0)) {  // experiment: DRAM -> L2 fetch granularity (32 / 64 / 128 bytes)
-        CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2g));
-        size_t got = 0;
-        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
-        if (env_int("SNP_HOST_TRACE", 0)) fprintf(stderr, "snappier_b200: L2 fetch granularity %zu\n", got);
-    }
     c->comp_kernel = env_int("SNP_COMP_KERNEL", 3);
     c->comp_ctas_per_sm = std::max(1, std::min(8, env_int("SNP_COMP_CTAS_PER_SM", 8)));
     c->comp_first_width = std::max(1, std::min(32, env_int("SNP_COMP_FIRST_WIDTH", 16)));
