@@ -211,6 +211,13 @@ int snp_pack_batch(snp_ctx *ctx, const uint8_t *src_base, const uint64_t *src_of
 int snp_find_match_length_batch(snp_ctx *ctx, const uint8_t *base, const uint32_t *s1, const uint32_t *s2,
                                 const uint32_t *s2_limit, uint32_t *matched, size_t n_items, void *stream);
 
+/* DIAGNOSTICS (not part of the reference's surface): measures the GPU's random-access read ceiling that bounds designs
+ * which turn back-references or hash-table probes into independent DRAM accesses.  sm_count x ctas_per_sm
+ * CTAs of 256 threads each issue reads_per_thread 16-byte loads at pseudo-random aligned offsets of [base, base +
+ * span_bytes) (DEVICE memory, 16-byte aligned).  Time it with events on `stream`; tools/random_access_probe.py does. */
+int snp_diag_random_reads(snp_ctx *ctx, const uint8_t *base, size_t span_bytes, uint32_t ctas_per_sm,
+                          uint32_t reads_per_thread, uint32_t *sink, void *stream);
+
 /* Batched Crc32CAlgorithm.Compute (+ ApplyMask when masked != 0), Crc32CAlgorithm.cs:41-44,157-158. */
 int snp_crc32c_batch(snp_ctx *ctx, const uint8_t *base, const uint64_t *off, const uint32_t *len,
                      uint32_t *crc, size_t n_items, int masked, int mem_kind, void *stream);

@@ -28,7 +28,7 @@ SYMBOLS = [
     "snp_compress", "snp_decompress", "snp_compress_sequence", "snp_decompress_sequence",
     "snp_compress_batch", "snp_decompress_batch", "snp_uncompressed_length_batch",
     "snp_frame_max_compressed_length", "snp_frame_compress", "snp_frame_uncompressed_length",
-    "snp_frame_decompress", "snp_crc32c_batch", "snp_pack_batch", "snp_find_match_length_batch",
+    "snp_frame_decompress", "snp_crc32c_batch", "snp_pack_batch", "snp_find_match_length_batch", "snp_diag_random_reads",
 ]
 
 _lib = None
@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
     L.snp_crc32c_batch.argtypes = [vp, vp, vp, vp, vp, sz, C.c_int, C.c_int, vp]
     L.snp_pack_batch.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp]
     L.snp_find_match_length_batch.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp]
+    L.snp_diag_random_reads.argtypes = [vp, vp, sz, u32, u32, vp, vp]
     _lib = L
     return L
 

@@ -350,6 +350,26 @@ __global__ void __launch_bounds__(256) k_find_match_length(const uint8_t *__rest
     }
 }
 
+// ---- diagnostics: the chip's random-access read ceiling ---------------------------------------------
+// Every thread issues `reads` dependent-free 16-byte loads at pseudo-random 16-byte-aligned offsets of [0, span) (an LCG per
+// thread; `ilp` loads in flight per thread), and folds them into a checksum so that nothing is optimised away.
+__global__ void __launch_bounds__(256) k_diag_random_reads(const uint4 *__restrict__ base, unsigned long long span16,
+                                                           uint32_t reads, uint32_t *__restrict__ sink) {
+    unsigned long long x = 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < reads; i += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            x = x * 6364136223846793005ull + 1442695040888963407ull;
+            v[k] = __ldcg(base + (x >> 17) % span16);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc += v[k].x ^ v[k].y ^ v[k].z ^ v[k].w;
+    }
+    if (acc == 0x12345679u) sink[0] = acc;  // practically never: keeps the loads alive
+}
+
 // ---- packing a batch: slots with slack -> dense bytes (the gather(v) side of block-range sharding, SURVEY.md 8(e);
 // the batched form of what Snappy.CompressToMemory returns: exactly the compressed bytes, no slack) --------------------
 // Exclusive scan of len[0..n) in three launches: per-CTA sums, scan of the sums (one CTA), per-CTA offsets.
@@ -1194,6 +1214,17 @@ int snp_find_match_length_batch(snp_ctx *c, const uint8_t *base, const uint32_t 
     const unsigned grid = (unsigned)std::min((n + 7) / 8, (size_t)c->sm_count * 8);
     k_find_match_length<<<grid, 256, 0, (cudaStream_t)stream>>>(base, s1, s2, s2_limit, matched, n);
     c->launches++;
+    CU(cudaGetLastError());
+    return SNP_OK;
+} SNP_ABI_CATCH
+
+int snp_diag_random_reads(snp_ctx *c, const uint8_t *base, size_t span_bytes, uint32_t ctas_per_sm, uint32_t reads_per_thread,
+                          uint32_t *sink, void *stream) try {
+    if (!c || !base || span_bytes < 16 || !sink || ctas_per_sm == 0 || ctas_per_sm > 8) return SNP_E_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard g(c->device);
+    k_diag_random_reads<<<(unsigned)(c->sm_count * ctas_per_sm), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4 *)base, (unsigned long long)(span_bytes / 16), reads_per_thread & ~3u, sink);
     CU(cudaGetLastError());
     return SNP_OK;
 } SNP_ABI_CATCH
